@@ -1,0 +1,191 @@
+/*
+ * cdprobe.h — C ABI of libcdprobe.so: the ComputeDomain fabric-validation probe.
+ *
+ * This is the drop-in boundary for the compute-domain-daemon's domain-ready
+ * gate.  The reference's gate is `check()` in
+ *   cmd/compute-domain-daemon/main.go:435-459
+ * (exec `nvidia-imex-ctl -q`, compare stdout with "READY\n"; a no-op when
+ * CLIQUE_ID is empty, main.go:436-439).  The reference has no NVLink probe
+ * (SURVEY.md F1); the functions below are what a Go shim `pkg/fabricprobe`
+ * binds over cgo so that `run()` (main.go:212-347) can
+ * execute an all-pairs NVLink reachability + bandwidth probe on the GPUs the
+ * daemon owns and `check()` can consult its verdict.
+ *
+ * Rules of the ABI:
+ *   - plain C, fixed-width integers, caller-allocated outputs, no pointers
+ *     cross back except the opaque handle;
+ *   - 0 = ok, <0 = cdprobe error enum (below); the CUDA/driver status that
+ *     caused a CDPROBE_ERR_CUDA is available from cdprobe_last_error();
+ *   - the library never prints and never aborts (klog owns stdout/stderr in
+ *     the daemon: cmd/compute-domain-daemon/process.go:92-96);
+ *   - a handle is not thread-safe; distinct handles are independent;
+ *   - there is NO CPU fallback: without a CUDA driver + sm_100 device
+ *     cdprobe_open() fails with CDPROBE_ERR_NO_DEVICE / _UNSUPPORTED.
+ *
+ * All integer results (reachability bits, checksums, schedule) are exact;
+ * GB/s values are measurements (run-to-run tolerance +-2 %, north_star).
+ */
+#ifndef CDPROBE_H_
+#define CDPROBE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CDPROBE_API __attribute__((visibility("default")))
+#else
+#define CDPROBE_API
+#endif
+
+#define CDPROBE_ABI_VERSION 1u
+#define CDPROBE_MAX_GPUS 16          /* ranks in one probe domain (8 on HGX B200) */
+#define CDPROBE_MAX_PHASES 64
+#define CDPROBE_NVLINK_MAX_LINKS 18  /* == NVML_NVLINK_MAX_LINKS (nvml.h:389) */
+
+/* Error enum (return values). */
+#define CDPROBE_OK 0
+#define CDPROBE_ERR_ABI (-1)         /* abi field mismatch */
+#define CDPROBE_ERR_ARG (-2)         /* invalid argument / config */
+#define CDPROBE_ERR_NO_DEVICE (-3)   /* no CUDA driver, or no usable GPU */
+#define CDPROBE_ERR_CUDA (-4)        /* a CUDA call failed; see cdprobe_last_error */
+#define CDPROBE_ERR_TIMEOUT (-5)     /* timeout_ms expired (device or host watchdog) */
+#define CDPROBE_ERR_RENDEZVOUS (-6)  /* multi-process handle exchange failed */
+#define CDPROBE_ERR_NOMEM (-7)
+#define CDPROBE_ERR_UNSUPPORTED (-8) /* device lacks VMM / cooperative launch / sm_100 */
+#define CDPROBE_ERR_STATE (-9)       /* handle unusable after a sticky CUDA error */
+#define CDPROBE_ERR_INTEGRITY (-10)  /* self-check of published checksums failed */
+
+/* cdprobe_config_t.mode — SURVEY.md §8(d) "Modes & algorithmic bytes". */
+#define CDPROBE_MODE_REACH_ONLY 0u   /* 64 KiB per ordered pair: latency floor */
+#define CDPROBE_MODE_SLICED 1u       /* bytes_per_pair = floor(B/(N-1)/128)*128 */
+#define CDPROBE_MODE_FULL 2u         /* bytes_per_pair = B */
+
+/* cdprobe_config_t.ops */
+#define CDPROBE_OP_READ 1u           /* rank i loads peer j's slice, checksums it */
+#define CDPROBE_OP_WRITE 2u          /* rank i stores a pattern into peer j; j verifies */
+
+/* cdprobe_config_t.flags */
+#define CDPROBE_FLAG_FABRIC_HANDLES 0x01u  /* CU_MEM_HANDLE_TYPE_FABRIC when /dev/nvidia-caps-imex-channels/channel0 opens */
+#define CDPROBE_FLAG_MIG_AWARE 0x02u       /* MIG devices: skip peer mapping, identity matrix */
+#define CDPROBE_FLAG_LOCAL_DIAG 0x04u      /* also measure the diagonal (loop-back into local HBM; always on when n == 1) */
+#define CDPROBE_FLAG_PATH_LDST 0x08u       /* 128-bit ld/st.global instead of TMA bulk copies */
+#define CDPROBE_FLAG_NO_COOPERATIVE 0x10u  /* plain launch (tests that put 2 ranks on one device) */
+#define CDPROBE_FLAG_OVERLAP_VERIFY 0x20u  /* verify landing slots on spare CTAs while the next round runs */
+#define CDPROBE_FLAG_ALLOW_SAME_DEVICE 0x40u /* several ranks may name the same CUDA ordinal (testing) */
+
+typedef struct cdprobe cdprobe_t;
+
+typedef struct {
+  uint32_t abi;                         /* CDPROBE_ABI_VERSION */
+  uint32_t n_gpus;                      /* GPUs driven by THIS process; 0 = all visible */
+  int32_t ordinals[CDPROBE_MAX_GPUS];   /* CUDA ordinals; ignored when n_gpus == 0 */
+  uint64_t bytes;                       /* B: per-GPU probe buffer (1 GiB for the headline config) */
+  uint32_t mode;                        /* CDPROBE_MODE_* */
+  uint32_t ops;                         /* CDPROBE_OP_* bits; 0 = read|write */
+  uint32_t timeout_ms;                  /* device + host watchdog; 0 = 5000 */
+  uint32_t flags;                       /* CDPROBE_FLAG_* */
+  uint64_t seed;                        /* 0 = 0xCD5EED0000000001 */
+  float min_fraction;                   /* verdict threshold on pair GB/s / link_peak; 0 = 0.85 */
+  float link_peak_gbps;                 /* 0 = 900 (NVLink 5, per direction per GPU) */
+  uint32_t ctas;                        /* CTAs of the persistent kernel; 0 = one per SM */
+  uint32_t world_size;                  /* processes in the probe domain; 0/1 = single process */
+  uint32_t rank;                        /* this process's index in [0, world_size) */
+  uint32_t reserved0;
+  char session[64];                     /* rendezvous name shared by all processes (world_size > 1) */
+} cdprobe_config_t;
+
+/* Matrices are row-major [issuer * CDPROBE_MAX_GPUS + target], issuer = the
+ * rank whose SMs issue the loads (read) or stores (write).  A process fills
+ * the rows of its local ranks (row_mask); cdprobe_gather() completes them. */
+typedef struct {
+  uint32_t abi;
+  uint32_t n;                           /* total ranks in the domain */
+  uint32_t row_mask;                    /* bit r set: row r is filled in */
+  uint32_t verdict;                     /* 1: every filled off-diagonal cell reachable and >= min_fraction */
+  uint8_t reach_read[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS];
+  uint8_t reach_write[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS];
+  float gbps_read[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS];
+  float gbps_write[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS];
+  int32_t status[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS]; /* 0 ok; <0 CDPROBE_ERR_*; >0 CUresult of the mapping */
+  uint64_t sum_read[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS];  /* checksum S the issuer computed (parity tests) */
+  uint64_t xor_read[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS];  /* checksum X */
+  uint64_t sum_write[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS]; /* checksum of the pattern the issuer generated */
+  uint64_t xor_write[CDPROBE_MAX_GPUS * CDPROBE_MAX_GPUS];
+  uint64_t bytes_per_pair;
+  uint64_t run_seq;                     /* 1-based count of cdprobe_run on this handle */
+  uint32_t rounds;                      /* tournament rounds (N-1 for even N) */
+  uint32_t phases;                      /* device phases executed */
+  uint32_t launches;                    /* kernels launched by this call (one per local rank) */
+  uint32_t aborted;                     /* 1: a device watchdog fired */
+  double probe_ms;                      /* host wall clock of this cdprobe_run call */
+  double device_ms[CDPROBE_MAX_GPUS];   /* per local rank: first barrier release -> last arrive (%globaltimer) */
+  double barrier_us[CDPROBE_MAX_GPUS];  /* per local rank: sum of (release - arrive) over all barriers */
+  float min_gbps_read;                  /* over filled off-diagonal cells (diagonal when n == 1) */
+  float min_gbps_write;
+} cdprobe_result_t;
+
+typedef struct {
+  uint32_t abi;
+  uint32_t n;                           /* total ranks */
+  uint32_t n_local;
+  uint32_t first_local_rank;
+  int32_t ordinal[CDPROBE_MAX_GPUS];    /* per local rank */
+  uint32_t sm_count[CDPROBE_MAX_GPUS];
+  uint32_t ctas[CDPROBE_MAX_GPUS];
+  uint32_t mig[CDPROBE_MAX_GPUS];
+  char uuid[CDPROBE_MAX_GPUS][48];      /* "GPU-xxxxxxxx-xxxx-xxxx-xxxx-xxxxxxxxxxxx" per local rank */
+  uint32_t handle_type;                 /* 0 none (in-process), 1 POSIX fd, 8 fabric */
+  uint32_t path;                        /* 0 TMA bulk, 1 ld/st */
+  uint64_t bytes_per_pair;
+  uint64_t alloc_bytes;                 /* HBM per rank */
+  uint64_t src_sum[CDPROBE_MAX_GPUS][CDPROBE_MAX_GPUS]; /* [local rank][slice]: device-computed checksum S of the source slices */
+  uint64_t src_xor[CDPROBE_MAX_GPUS][CDPROBE_MAX_GPUS];
+  uint32_t n_slices;
+  uint32_t smem_bytes;
+  double open_ms;                       /* contexts + VMM + mapping */
+  double fill_ms;                       /* pattern fill + slice checksums */
+} cdprobe_info_t;
+
+/* Plan (host-only arithmetic; usable without a GPU). */
+typedef struct {
+  uint32_t abi;
+  uint32_t n;
+  uint32_t rounds;
+  uint32_t n_slots;                     /* landing slots per rank */
+  uint32_t n_slices;                    /* source slices per rank */
+  uint32_t reserved;
+  uint64_t bytes_per_pair;
+  uint64_t src_bytes;
+  uint64_t land_bytes;
+  int8_t partner[CDPROBE_MAX_GPUS][CDPROBE_MAX_GPUS]; /* [round][rank], -1 = idle */
+} cdprobe_plan_t;
+
+CDPROBE_API uint32_t cdprobe_abi_version(void);
+CDPROBE_API const char* cdprobe_strerror(int code);
+/* Detail of the last failure on the calling thread ("cuMemMap: CUDA_ERROR_..."), "" if none. */
+CDPROBE_API const char* cdprobe_last_error(void);
+
+CDPROBE_API int cdprobe_open(const cdprobe_config_t* cfg, cdprobe_t** out);
+CDPROBE_API int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out);
+/* Collective over all processes of the domain: completes rows of other processes. No-op for world_size <= 1. */
+CDPROBE_API int cdprobe_gather(cdprobe_t* h, cdprobe_result_t* inout);
+CDPROBE_API int cdprobe_info(cdprobe_t* h, cdprobe_info_t* out);
+/* Storm/unprepare emulation: unmap + remap rank `peer` in local rank `local`'s address space. */
+CDPROBE_API int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer);
+/* Fault injection for parity tests: drop local rank's mapping of `peer` (cell becomes unreachable, run still returns). */
+CDPROBE_API int cdprobe_unmap_peer(cdprobe_t* h, uint32_t local, uint32_t peer);
+/* Fault injection: XOR one 64-bit word of local rank's source slice / force a bad write salt. */
+CDPROBE_API int cdprobe_corrupt(cdprobe_t* h, uint32_t local, uint64_t byte_offset, uint64_t xor_mask);
+CDPROBE_API void cdprobe_close(cdprobe_t* h);
+
+/* Host-only helpers (no CUDA): schedule + slice arithmetic; the fd/blob rendezvous self-test. */
+CDPROBE_API int cdprobe_plan(uint32_t n, uint64_t bytes, uint32_t mode, uint32_t flags, cdprobe_plan_t* out);
+CDPROBE_API int cdprobe_rendezvous_selftest(const char* session, uint32_t rank, uint32_t world, uint32_t timeout_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDPROBE_H_ */
