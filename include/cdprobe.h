@@ -123,6 +123,8 @@ typedef struct {
   double probe_ms;                      /* host wall clock of this cdprobe_run call */
   double device_ms[CDPROBE_MAX_GPUS];   /* per local rank: first barrier release -> last arrive (%globaltimer) */
   double barrier_us[CDPROBE_MAX_GPUS];  /* per local rank: sum of (release - arrive) over all barriers */
+  double event_ms[CDPROBE_MAX_GPUS];    /* per local rank: kernel duration by CUDA events on the launch stream
+                                           (only with CDPROBE_OPT_EVENT_TIMING; 0 otherwise) */
   float min_gbps_read;                  /* over filled off-diagonal cells (diagonal when n == 1) */
   float min_gbps_write;
 } cdprobe_result_t;
@@ -173,6 +175,13 @@ CDPROBE_API int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out);
 /* Collective over all processes of the domain: completes rows of other processes. No-op for world_size <= 1. */
 CDPROBE_API int cdprobe_gather(cdprobe_t* h, cdprobe_result_t* inout);
 CDPROBE_API int cdprobe_info(cdprobe_t* h, cdprobe_info_t* out);
+/* Runtime options (no reopen needed; the bench sweeps them). */
+#define CDPROBE_OPT_EVENT_TIMING 1u  /* value 0/1: bracket each kernel with CUDA events, report event_ms */
+#define CDPROBE_OPT_CTAS 2u          /* CTAs of the persistent kernel (0 = one per SM) */
+#define CDPROBE_OPT_PATH 3u          /* 0 = TMA bulk copies, 1 = ld/st.global.v4 */
+#define CDPROBE_OPT_TIMEOUT_MS 4u
+#define CDPROBE_OPT_OVERLAP_VERIFY 5u /* value 0/1 */
+CDPROBE_API int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value);
 /* Storm/unprepare emulation: unmap + remap rank `peer` in local rank `local`'s address space. */
 CDPROBE_API int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer);
 /* Fault injection for parity tests: drop local rank's mapping of `peer` (cell becomes unreachable, run still returns). */

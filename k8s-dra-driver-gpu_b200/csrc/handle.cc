@@ -55,6 +55,8 @@ struct LocalRank {
   bool coop = false;
   bool mig = false;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int max_ctas = 0;
   CUmemGenericAllocationHandle own = 0;
   bool has_own = false;
   int own_fd = -1;
@@ -87,6 +89,7 @@ struct cdprobe {
   uint64_t src_sum[kMaxRanks][kMaxRanks] = {};
   uint64_t src_xor[kMaxRanks][kMaxRanks] = {};
   bool sticky = false;
+  bool event_timing = false;
   double open_ms = 0, fill_ms = 0;
 };
 
@@ -389,6 +392,8 @@ static void destroy(cdprobe* h) {
     if (L.has_own) h->drv.MemRelease(L.own);
     if (L.own_fd >= 0) ::close(L.own_fd);
     if (L.row) cudaFreeHost(L.row);
+    if (L.ev0) cudaEventDestroy(L.ev0);
+    if (L.ev1) cudaEventDestroy(L.ev1);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   h->rdv.close();
@@ -505,7 +510,10 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
     if (ctas > cap) ctas = cap;
     if (ctas > 65535u) ctas = 65535u;
     L.ctas = ctas;
+    L.max_ctas = (int)(cap > 65535u ? 65535u : cap);
     CDP_RT(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    CDP_RT(cudaEventCreate(&L.ev0));
+    CDP_RT(cudaEventCreate(&L.ev1));
 
     CUmemAllocationProp ap;
     memset(&ap, 0, sizeof(ap));
@@ -752,11 +760,16 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
   for (uint32_t li = 0; li < h->n_local; ++li) {
     cdp::LocalRank& L = h->lr[li];
     cdp::fill_params(h, li, L.phases, L.n_phases, L.peer_mask, &P);
+    if (h->event_timing) {
+      cudaSetDevice(L.ordinal);
+      cudaEventRecord(L.ev0, L.stream);
+    }
     const int rc = cdp::launch_one(h, li, P);
     if (rc != CDPROBE_OK) {
       h->sticky = true;
       return rc;
     }
+    if (h->event_timing) cudaEventRecord(L.ev1, L.stream);
     out->launches++;
     out->phases = L.n_phases;
   }
@@ -768,6 +781,15 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
   }
   cdp::assemble(h, out);
   out->probe_ms = cdp::now_ms() - t0;
+  if (h->event_timing) {  // after probe_ms: the event round trip is not part of the probe
+    for (uint32_t li = 0; li < h->n_local; ++li) {
+      cdp::LocalRank& L = h->lr[li];
+      float ms = 0.f;
+      cudaSetDevice(L.ordinal);
+      if (cudaEventSynchronize(L.ev1) == cudaSuccess && cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess)
+        out->event_ms[li] = ms;
+    }
+  }
   if (out->aborted) {
     for (uint32_t li = 0; li < h->n_local; ++li) {
       const int rc = cdp::reset_ctrl_local(h, li);
@@ -847,6 +869,38 @@ int cdprobe_info(cdprobe_t* h, cdprobe_info_t* out) {
   out->open_ms = h->open_ms;
   out->fill_ms = h->fill_ms;
   return CDPROBE_OK;
+}
+
+int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
+  if (h == nullptr) return CDPROBE_ERR_ARG;
+  switch (option) {
+    case CDPROBE_OPT_EVENT_TIMING:
+      h->event_timing = value != 0;
+      return CDPROBE_OK;
+    case CDPROBE_OPT_CTAS:
+      for (uint32_t li = 0; li < h->n_local; ++li) {
+        cdp::LocalRank& L = h->lr[li];
+        uint32_t c = value ? (uint32_t)value : (uint32_t)L.sm_count;
+        if (c > (uint32_t)L.max_ctas) c = (uint32_t)L.max_ctas;
+        L.ctas = c;
+        cdp::build_phases(h, li);
+      }
+      return CDPROBE_OK;
+    case CDPROBE_OPT_PATH:
+      if (value > 1) return CDPROBE_ERR_ARG;
+      h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_PATH_LDST) | (value ? CDPROBE_FLAG_PATH_LDST : 0u);
+      return CDPROBE_OK;
+    case CDPROBE_OPT_TIMEOUT_MS:
+      if (value == 0 || value > 600000) return CDPROBE_ERR_ARG;
+      h->cfg.timeout_ms = (uint32_t)value;
+      return CDPROBE_OK;
+    case CDPROBE_OPT_OVERLAP_VERIFY:
+      h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_OVERLAP_VERIFY) | (value ? CDPROBE_FLAG_OVERLAP_VERIFY : 0u);
+      for (uint32_t li = 0; li < h->n_local; ++li) cdp::build_phases(h, li);
+      return CDPROBE_OK;
+    default:
+      return CDPROBE_ERR_ARG;
+  }
 }
 
 int cdprobe_unmap_peer(cdprobe_t* h, uint32_t local, uint32_t peer) {

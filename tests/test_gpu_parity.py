@@ -1,0 +1,287 @@
+"""Parity tests proper: the CUDA probe (through the C ABI, ctypes) against the CPU oracle.
+
+Bit-exact bar: reachability bits, (S, X) checksums of every slice read or written, the
+published source checksums.  GB/s values are measurements (positive, finite; +-2 % run to
+run is checked by bench.py, not here).
+
+Small sizes are compared with the oracle's scalar restatement; BASELINE.json's full sizes
+(1 GiB, 64 MiB) through the same checksums (the oracle streams 1 GiB in about a second) plus
+size-independent properties: write->verify round trip, corruption is detected, a torn-down
+mapping yields a 0 cell and the run still returns, run_seq salts make stale data fail.
+"""
+import json
+import subprocess
+import sys
+import textwrap
+import uuid
+
+import pytest
+
+from conftest import ROOT, gpu_count
+
+pytestmark = pytest.mark.gpu
+
+NGPU = gpu_count()
+SEED = 0xCD5EED0000000001
+
+
+def expected_read(oracle, n, nbytes, mode, i, j, diag=False):
+    return oracle.expected_read(SEED, n, nbytes, mode, i, j, diag)
+
+
+def check_full_parity(pkg, oracle, res, n, nbytes, mode, ops, diag=False):
+    bpp = res.bytes_per_pair
+    assert bpp == oracle.plan(n, nbytes, mode, diag).bytes_per_pair
+    for i in range(n):
+        if not (res.row_mask >> i) & 1:
+            continue
+        for j in range(n):
+            if i == j and not (diag or n == 1):
+                assert res.reach_read[i][j] == 1 and res.reach_write[i][j] == 1
+                continue
+            if ops & pkg.abi.OP_READ:
+                assert res.reach_read[i][j] == 1, (i, j)
+                assert (res.sum_read[i][j], res.xor_read[i][j]) == expected_read(oracle, n, nbytes, mode, i, j, diag), (i, j)
+                assert res.gbps_read[i][j] > 0
+            if ops & pkg.abi.OP_WRITE:
+                assert res.reach_write[i][j] == 1, (i, j)
+                exp = oracle.write_checksum(SEED, i, j, res.run_seq, bpp // 8)
+                assert (res.sum_write[i][j], res.xor_write[i][j]) == exp, (i, j)
+                assert res.gbps_write[i][j] > 0
+
+
+# ------------------------------------------------------------------ N = 1 loop-back ----
+@pytest.mark.parametrize("path_flag", [0, 0x08], ids=["tma", "ldst"])
+@pytest.mark.parametrize("nbytes", [128, 8192, 8192 + 128, 16384 * 3 + 640, 1 << 20, (1 << 23) + 128 * 77])
+def test_single_gpu_small_sizes(pkg, oracle, nbytes, path_flag):
+    with pkg.Open(pkg.Config(ordinals=[0], bytes=nbytes, mode=pkg.abi.MODE_SLICED, flags=path_flag)) as p:
+        info = p.Info()
+        assert info.n == 1 and info.n_slices == 1
+        exp = oracle.src_checksum(SEED, 0, 0, nbytes // 128 * 128 // 8)
+        assert (info.src_sum[0][0], info.src_xor[0][0]) == exp  # device-published == oracle
+        for _ in range(3):
+            r = p.Run()
+            assert r.verdict and not r.aborted and r.launches == 1
+            check_full_parity(pkg, oracle, r, 1, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
+@pytest.mark.parametrize("path_flag", [0, 0x08], ids=["tma", "ldst"])
+def test_single_gpu_one_gib(pkg, oracle, path_flag):
+    """BASELINE config at one GPU: 1 GiB buffer, read + write + verify, checksums bit-exact."""
+    nbytes = 1 << 30
+    with pkg.Open(pkg.Config(ordinals=[0], bytes=nbytes, flags=path_flag)) as p:
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, 1, nbytes, pkg.abi.MODE_SLICED, 3)
+        assert r.verdict
+        r2 = p.Run()
+        # a new run re-salts the write pattern: same read checksums, different write checksums
+        assert r2.sum_read[0][0] == r.sum_read[0][0] and r2.sum_write[0][0] != r.sum_write[0][0]
+        check_full_parity(pkg, oracle, r2, 1, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("ops", [1, 2, 3])
+def test_single_gpu_modes_and_ops(pkg, oracle, mode, ops):
+    nbytes = 4 << 20
+    with pkg.Open(pkg.Config(ordinals=[0], bytes=nbytes, mode=mode, ops=ops)) as p:
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, 1, nbytes, mode, ops)
+
+
+def test_corruption_is_detected(pkg, oracle):
+    nbytes = 1 << 20
+    with pkg.Open(pkg.Config(ordinals=[0], bytes=nbytes)) as p:
+        assert p.Run().verdict
+        p.Corrupt(0, 4096 + 8, 1 << 17)  # flip one bit of one word of the source buffer
+        r = p.Run()
+        assert r.reach_read[0][0] == 0 and r.reach_write[0][0] == 1 and not r.verdict
+        p.Corrupt(0, 4096 + 8, 1 << 17)  # flip it back
+        assert p.Run().verdict
+
+
+def test_small_grid_and_many_runs(pkg, oracle):
+    """Storm-lite (config 5): one handle, many runs, a non-default grid; results stay exact."""
+    nbytes = 3 << 20
+    with pkg.Open(pkg.Config(ordinals=[0], bytes=nbytes, ctas=5)) as p:
+        assert p.Info().ctas[0] == 5
+        seqs = []
+        for _ in range(40):
+            r = p.Run()
+            seqs.append(r.run_seq)
+            assert r.verdict
+        assert seqs == list(range(seqs[0], seqs[0] + 40))
+        check_full_parity(pkg, oracle, r, 1, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
+# --------------------------------------------- several ranks on one device (one process) ----
+SAME = 0x40 | 0x10  # ALLOW_SAME_DEVICE | NO_COOPERATIVE
+
+
+@pytest.mark.parametrize("path_flag", [0, 0x08], ids=["tma", "ldst"])
+@pytest.mark.parametrize("n,mode", [(2, 1), (2, 2), (3, 1), (4, 1), (4, 0), (5, 1), (8, 1)])
+def test_same_device_ranks(pkg, oracle, n, mode, path_flag):
+    """The whole multi-rank machinery (tournament, peer mappings, cross-rank flag barrier,
+    write -> publish -> verify -> verdict) with every rank on GPU 0: works on a 1-GPU box."""
+    nbytes = 2 << 20
+    cfg = pkg.Config(ordinals=[0] * n, bytes=nbytes, mode=mode, flags=SAME | path_flag, ctas=8, timeout_ms=20000)
+    with pkg.Open(cfg) as p:
+        for _ in range(2):
+            r = p.Run()
+            assert r.n == n and r.row_mask == (1 << n) - 1 and r.launches == n
+            assert not r.aborted
+            check_full_parity(pkg, oracle, r, n, nbytes, mode, 3)
+            assert r.reach == [[1] * n for _ in range(n)]
+            assert r.rounds == (n if n % 2 else n - 1)
+
+
+def test_same_device_with_diagonal(pkg, oracle):
+    n, nbytes = 4, 1 << 20
+    cfg = pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME | pkg.abi.FLAG_LOCAL_DIAG, ctas=8, timeout_ms=20000)
+    with pkg.Open(cfg) as p:
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3, diag=True)
+
+
+def test_unmapped_peer_gives_zero_cell_and_run_returns(pkg, oracle):
+    """Fault injection: drop rank 1's mapping of rank 2 => cells (1,2) and
+    (2,1) are unreachable (a pair needs both directions for its barrier and verdict), every
+    other cell stays 1 and the run still returns; remap heals it."""
+    n, nbytes = 4, 1 << 20
+    cfg = pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)
+    with pkg.Open(cfg) as p:
+        assert p.Run().reach == [[1] * n for _ in range(n)]
+        p.UnmapPeer(1, 2)
+        r = p.Run()
+        exp = [[1] * n for _ in range(n)]
+        exp[1][2] = exp[2][1] = 0
+        assert r.reach == exp and not r.verdict and not r.aborted
+        assert r.status[1][2] != 0
+        p.RemapPeer(1, 2)
+        r = p.Run()
+        assert r.reach == [[1] * n for _ in range(n)]
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
+def test_corrupt_one_slice_hits_exactly_one_reader(pkg, oracle):
+    n, nbytes = 4, 1 << 20
+    cfg = pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)
+    with pkg.Open(cfg) as p:
+        bpp = p.Info().bytes_per_pair
+        # slice 1 of rank 0's source is what rank 2 reads (its slot among rank 0's peers)
+        p.Corrupt(0, bpp + 64, 0xFF)
+        r = p.Run()
+        exp = [[1] * n for _ in range(n)]
+        exp[2][0] = 0
+        assert r.reach_read == exp
+        assert r.reach_write == [[1] * n for _ in range(n)]
+
+
+# ------------------------------------------------ one process per rank (bench.py's layout) ----
+CHILD = textwrap.dedent(
+    """
+    import json, sys
+    sys.path.insert(0, %r)
+    import cdprobe_pkg
+    m = cdprobe_pkg.load()
+    session, rank, world, ordinal, nbytes, flags = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+    cfg = m.Config(ordinals=[ordinal], bytes=nbytes, world_size=world, rank=rank, session=session, flags=flags,
+                   ctas=int(sys.argv[7]), timeout_ms=30000)
+    with m.Open(cfg) as p:
+        info = p.Info()
+        out = []
+        for _ in range(2):
+            r = p.Run(gather=True)
+            out.append({"n": r.n, "row_mask": r.row_mask, "reach_read": r.reach_read, "reach_write": r.reach_write,
+                        "sum_read": r.sum_read, "xor_read": r.xor_read, "sum_write": r.sum_write,
+                        "xor_write": r.xor_write, "run_seq": r.run_seq, "bpp": r.bytes_per_pair,
+                        "verdict": r.verdict, "aborted": r.aborted, "handle_type": info.handle_type})
+    print("RESULT " + json.dumps(out))
+    """
+) % ROOT
+
+
+def run_world(world, ordinals, nbytes, flags, ctas):
+    session = f"g-{uuid.uuid4().hex[:12]}"
+    procs = [subprocess.Popen([sys.executable, "-c", CHILD, session, str(r), str(world), str(ordinals[r]), str(nbytes),
+                               str(flags), str(ctas)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(world)]
+    outs = []
+    for p in procs:
+        so, se = p.communicate(timeout=300)
+        assert p.returncode == 0, se[-2000:]
+        outs.append(json.loads([l for l in so.splitlines() if l.startswith("RESULT ")][-1][7:]))
+    return outs
+
+
+def check_world(oracle, outs, world, nbytes):
+    for per_rank in outs:
+        for r in per_rank:
+            assert r["n"] == world and r["row_mask"] == (1 << world) - 1 and not r["aborted"]
+            assert r["handle_type"] == 1  # POSIX fd handles crossed the process boundary
+            for i in range(world):
+                for j in range(world):
+                    if i == j:
+                        continue
+                    assert r["reach_read"][i][j] == 1 and r["reach_write"][i][j] == 1
+                    assert (r["sum_read"][i][j], r["xor_read"][i][j]) == expected_read(oracle, world, nbytes, 1, i, j)
+                    assert (r["sum_write"][i][j], r["xor_write"][i][j]) == oracle.write_checksum(
+                        SEED, i, j, r["run_seq"], r["bpp"] // 8)
+    # after cdprobe_gather every process holds the same matrices
+    assert all(o == outs[0] for o in outs[1:])
+
+
+def test_two_processes_share_one_gpu(pkg, oracle):
+    """world_size = 2, both on GPU 0: cuMem fd export/import over the unix socket, peer mapping of an
+    imported handle, the flag barrier across two contexts (time-sliced, hence the long timeout)."""
+    nbytes = 1 << 20
+    outs = run_world(2, [0, 0], nbytes, 0x40, 8)
+    check_world(oracle, outs, 2, nbytes)
+
+
+# ----------------------------------------------------------------- real multi-GPU boxes ----
+@pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("path_flag", [0, 0x08], ids=["tma", "ldst"])
+def test_multi_gpu_in_process_parity_with_nvml_oracle(pkg, oracle, path_flag):
+    """Config 2/3: every visible GPU in one domain; reach_read & reach_write must equal the NVML
+    oracle's matrix bit for bit (matched by UUID), checksums equal the pattern oracle."""
+    n = min(NGPU, 8)
+    nbytes = 64 << 20
+    with pkg.Open(pkg.Config(ordinals=list(range(n)), bytes=nbytes, mode=pkg.abi.MODE_SLICED, flags=path_flag,
+                             timeout_ms=20000)) as p:
+        info = p.Info()
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+        o = oracle.nvml_poll()
+        by_uuid = {u: k for k, u in enumerate(o.uuids())}
+        idx = [by_uuid[info.uuid[i].value.decode()] for i in range(n)]
+        om = o.reach_matrix()
+        exp = [[om[idx[i]][idx[j]] for j in range(n)] for i in range(n)]
+        assert r.reach == exp
+        assert r.reach == [[1] * n for _ in range(n)]  # an HGX B200 box is fully connected
+
+
+@pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
+def test_config2_two_gpu_64mib_full(pkg, oracle):
+    """BASELINE config 2: 2-GPU P2P read/write reachability matrix, 64 MiB buffers, full mode."""
+    nbytes = 64 << 20
+    flags = pkg.abi.FLAG_FABRIC_HANDLES  # fabric handles iff IMEX channel 0 exists, else plain VMM
+    with pkg.Open(pkg.Config(ordinals=[0, 1], bytes=nbytes, mode=pkg.abi.MODE_FULL, flags=flags)) as p:
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, 2, nbytes, pkg.abi.MODE_FULL, 3)
+        assert r.reach == [[1, 1], [1, 1]] and r.rounds == 1
+
+
+@pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
+def test_multi_gpu_one_process_per_gpu(pkg, oracle):
+    n = min(NGPU, 8)
+    nbytes = 32 << 20
+    outs = run_world(n, list(range(n)), nbytes, 0, 0)
+    check_world(oracle, outs, n, nbytes)
+
+
+def test_nvml_oracle_runs_on_this_box(oracle):
+    """The CPU baseline leg itself: real libnvidia-ml.so.1, config 1 (enumerate + NvLinkState poll)."""
+    o = oracle.nvml_poll()
+    assert o.n >= 1 and o.nvml_calls >= 18 * o.n
+    assert all(o.reach[i * 16 + i] == 1 for i in range(o.n))
+    assert o.cc_major[0] == 10

@@ -1,0 +1,41 @@
+"""The multi-process control plane (fd passing + blobs + barrier over an abstract unix socket),
+exercised without CUDA by cdprobe_rendezvous_selftest: every rank shares a memfd and reads
+every other rank's.  This is the N>1 host path bench.py uses under torchrun."""
+import os
+import subprocess
+import sys
+import textwrap
+import uuid
+
+import pytest
+
+from conftest import ROOT
+
+CHILD = textwrap.dedent(
+    """
+    import sys
+    sys.path.insert(0, %r)
+    import cdprobe_pkg
+    m = cdprobe_pkg.load()
+    lib = m.abi.load_library()
+    sys.exit(-lib.cdprobe_rendezvous_selftest(sys.argv[1].encode(), int(sys.argv[2]), int(sys.argv[3]), 20000))
+    """
+) % ROOT
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_fd_exchange(pkg, world):
+    session = f"t-{uuid.uuid4().hex[:12]}"
+    procs = [subprocess.Popen([sys.executable, "-c", CHILD, session, str(r), str(world)]) for r in range(world)]
+    codes = [p.wait(timeout=120) for p in procs]
+    assert codes == [0] * world
+
+
+def test_missing_peer_times_out(pkg):
+    lib = pkg.abi.load_library()
+    # world of 2 but nobody else shows up: clean error, no hang
+    rc = lib.cdprobe_rendezvous_selftest(f"t-{uuid.uuid4().hex[:12]}".encode(), 0, 2, 300)
+    assert rc == pkg.abi.ERR_RENDEZVOUS
+    rc = lib.cdprobe_rendezvous_selftest(f"t-{uuid.uuid4().hex[:12]}".encode(), 1, 2, 300)
+    assert rc == pkg.abi.ERR_RENDEZVOUS
+    assert lib.cdprobe_rendezvous_selftest(b"x", 3, 2, 100) == pkg.abi.ERR_ARG
