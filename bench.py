@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""bench.py — the ComputeDomain fabric probe benchmark (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA probe
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU/NVML poll
+
+A "step" is one pass of the hot path: one `cdprobe_run` over the N-GPU domain (sliced mode,
+1 GiB per GPU, read + write + verify) — BASELINE.json configs[2] at N GPUs; at N = 1 the same
+kernel runs its loop-back phases against local HBM.  One process per GPU (torchrun for N > 1);
+the data path is NVLink P2P between cuMem-mapped buffers with a hand-rolled device barrier —
+torch.distributed (NCCL) is used only to bracket the timed region and take max-over-ranks.
+
+metric  = nvlink_probe_ms (lower is better): time to produce the N x N reachability + GB/s
+          matrix.  `value` is the probe kernel's duration by CUDA events on its launch stream
+          (max over ranks; buffers resident in HBM); `e2e.value` is the same probe through the
+          public C ABI call from the host: launch, kernel, result rows written to pinned host
+          memory and read back.  Per-pair GB/s vs the 900 GB/s/dir NVLink-5 peak is in
+          `per_link_gbps`; `roofline` is the dominant kernel against its bound (HBM at N = 1,
+          NVLink at N > 1).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GIB = 1 << 30
+NVLINK_PEAK_GBPS = 900.0        # nominal per direction per GPU
+NVLINK_MEASURED_GBPS = 770.0    # measured peer copy per direction (B200_PROFILING.md)
+HBM_FALLBACK_GBPS = 6650.0
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": HBM_FALLBACK_GBPS}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "samples": len(self.samples),
+            "reasons": sorted(self.reasons),
+        }
+
+
+def nvlink_counters(index: int):
+    """Aggregate NVLink data TX/RX KiB of one GPU (NVML field values 138/139), or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        out = {}
+        for name, fid in (("tx_kib", 138), ("rx_kib", 139)):
+            vals = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])
+            v = vals[0]
+            if v.nvmlReturn != 0:
+                return None
+            out[name] = int(v.value.ullVal)
+        return out
+    except Exception:
+        return None
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------- reference arm ----
+def cpu_poll_timing(n_gpus: int, steps: int, warmup: int, budget_s: float):
+    """Times the reference's CPU path (oracle/nvml_poll.c: the NVML enumerate + NvLinkState + P2PStatus
+    poll the north_star names) on this box's host cores.  Single-threaded: NVML serialises in the RM."""
+    from oracle import oracle as o
+
+    o.build()
+    times, last = [], None
+    t_stop = time.perf_counter() + budget_s
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        last = o.nvml_poll(n_gpus)
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() > t_stop and len(times) >= 3:
+            break
+    return times, last
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    line = {"impl": "reference", "metric": "nvlink_probe_ms", "unit": "ms", "n_gpus": args.gpus,
+            "higher_is_better": False, "data": "synthetic", "dtype": "u64", "vs_baseline": None, "scaling": "weak",
+            "gpu_launches": 0}
+    try:
+        times, last = cpu_poll_timing(args.gpus, args.steps, args.warmup, budget_s=120.0)
+    except Exception as e:  # NVML missing etc.: say so, do not fake a number
+        line["unavailable"] = f"NVML poll could not run: {e}"
+        print(json.dumps(line))
+        return 0
+    v = statistics.mean(times)
+    sample = (f"{len(times)} polls of the {last.n}-GPU node: nvmlInitWithFlags + enumerate + fabric info + "
+              f"{18 * last.n} NvLinkState + {3 * last.n * (last.n - 1)} P2PStatus + nvmlShutdown "
+              f"({last.nvml_calls} NVML calls per poll)")
+    line.update({
+        "value": v, "ms_per_step": v, "steps": len(times), "warmup": args.warmup,
+        "config": {"workload": f"reference CPU path: NVML link/P2P reachability poll, {last.n} GPU(s)",
+                   "n_gpus_polled": last.n, "threads": 1},
+        "cpu_baseline": {"value": v, "unit": "ms", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(), "median_ms": statistics.median(times),
+                         "max_ms": max(times),
+                         "phases_ms": {"init": last.init_ms, "enumerate": last.enumerate_ms, "fabric": last.fabric_ms,
+                                       "link_poll": last.link_poll_ms, "p2p_poll": last.p2p_poll_ms,
+                                       "shutdown": last.shutdown_ms}},
+        "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reach_all_ones": all(last.reach[i * 16 + j] for i in range(last.n) for j in range(last.n)),
+    })
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm ----
+def run_probe(args):
+    import torch
+
+    import cdprobe_pkg
+
+    pkg = cdprobe_pkg.load()
+    abi = pkg.abi
+    rank, world, local = dist_env()
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch N > 1 with torchrun: one process per GPU")
+    n = args.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    grp = pkg.distutil.RankGroup(backend="nccl", device=dev)
+
+    def barrier():
+        grp.barrier()
+        torch.cuda.synchronize()
+
+    max_over_ranks = grp.max
+
+    session = grp.session()
+    flags = abi.FLAG_PATH_LDST if args.path == "ldst" else 0
+    cfg = pkg.Config(ordinals=[local], bytes=args.bytes, mode={"sliced": 1, "full": 2, "reach": 0}[args.mode],
+                     ops=3, flags=flags, ctas=args.ctas, world_size=world, rank=rank, session=session,
+                     timeout_ms=args.timeout_ms)
+    probe = pkg.Open(cfg)
+    info = probe.Info()
+    out = abi.ResultT()
+
+    def step():
+        rc = probe.run_raw(out)
+        if rc != abi.OK:
+            raise RuntimeError(f"cdprobe_run rc={rc}: {abi.load_library().cdprobe_last_error().decode()}")
+
+    # ---- warm-up (untimed) --------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    nvl0 = nvlink_counters(local) if n > 1 else None
+
+    # ---- loop A: kernel durations by CUDA events on the launch stream -> `value`, roofline
+    probe.SetOption(abi.OPT_EVENT_TIMING, 1)
+    step()
+    ev, dev_ms, rd, wr = [], [], [], []
+    barrier()
+    for _ in range(args.steps):
+        step()
+        ev.append(out.event_ms[0])
+        dev_ms.append(out.device_ms[0])
+        rd.append(out.min_gbps_read)
+        wr.append(out.min_gbps_write)
+    barrier()
+    probe.SetOption(abi.OPT_EVENT_TIMING, 0)
+
+    # ---- loop B: EXACTLY K steps through the public ABI, barrier + sync on both sides -> e2e
+    step()
+    host_ms = []
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        host_ms.append(out.probe_ms)
+    torch.cuda.synchronize()
+    t_local = (time.perf_counter() - t0) * 1e3
+    barrier()
+    nvl1 = nvlink_counters(local) if n > 1 else None
+    clocks = sampler.stop()
+
+    wall_ms = max_over_ranks(t_local)
+    ms_per_step = wall_ms / args.steps
+    value = max_over_ranks(statistics.mean(ev))
+    device_ms = max_over_ranks(statistics.mean(dev_ms))
+    e2e_ms = max_over_ranks(statistics.mean(host_ms))
+
+    # per-pair GB/s over the whole domain (one extra, gathered run)
+    res = probe.Run(gather=True)
+    bpp = res.bytes_per_pair
+    pairs_r = [res.gbps_read[i][j] for i in range(n) for j in range(n) if i != j or n == 1]
+    pairs_w = [res.gbps_write[i][j] for i in range(n) for j in range(n) if i != j or n == 1]
+    reach_ok = all(res.reach[i][j] == 1 for i in range(n) for j in range(n))
+    spread_r = (max(rd) - min(rd)) / statistics.median(rd) if rd and statistics.median(rd) > 0 else None
+    spread_w = (max(wr) - min(wr)) / statistics.median(wr) if wr and statistics.median(wr) > 0 else None
+    spread_r = max_over_ranks(spread_r or 0.0)
+    spread_w = max_over_ranks(spread_w or 0.0)
+
+    peaks, peak_kind = measured_peaks()
+    passes = 3  # read B, write B, verify B per GPU per probe
+    a_gpu = (n - 1 if n > 1 else 1) * bpp
+    algo_bytes = passes * a_gpu  # per launch (= per GPU per probe)
+    achieved = algo_bytes / (value * 1e-3) / 1e9
+    if n == 1:
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": f"{peak_kind} copy bandwidth",
+                    "kernel": "cdprobe_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                    "note": "N=1 loop-back: read 1 GiB + write 1 GiB + verify 1 GiB of local HBM per launch"}
+    else:
+        # NVLink-bound phases: read (ingress) and write (egress) each move a_gpu bytes per GPU; verify is local
+        link_bytes = 2 * a_gpu
+        link_achieved = min(min(pairs_r), min(pairs_w))
+        roofline = {"bound": "nvlink", "achieved": link_achieved, "peak": NVLINK_PEAK_GBPS, "unit": "GB/s",
+                    "frac": link_achieved / NVLINK_PEAK_GBPS, "traffic": None,
+                    "peak_kind": "nominal NVLink 5 per direction per GPU (measured peer copy: 770 GB/s)",
+                    "frac_of_measured_770": link_achieved / NVLINK_MEASURED_GBPS,
+                    "kernel": "cdprobe_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                    "nvlink_bytes_per_launch_per_direction": a_gpu,
+                    "aggregate_link_gbps_per_gpu": link_bytes / (value * 1e-3) / 1e9,
+                    "note": "achieved = slowest ordered pair with exclusive endpoints (tournament round)"}
+
+    if rank == 0:
+        line = {
+            "metric": "nvlink_probe_ms", "value": value, "unit": "ms", "n_gpus": n, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {
+                "workload": (f"{n}-GPU all-pairs NVLink probe, {args.mode} mode, {args.bytes >> 20} MiB per GPU, "
+                             f"read+write+verify (BASELINE configs[2] at {n} GPU)" if n > 1 else
+                             f"1-GPU loop-back probe, {args.bytes >> 20} MiB buffer, read+write+verify"),
+                "bytes_per_gpu": args.bytes, "bytes_per_pair": bpp, "mode": args.mode, "path": args.path,
+                "ctas": int(info.ctas[0]), "rounds": res.rounds, "phases": res.phases,
+                "parallelism": f"{n} ranks, one process per GPU, no data-path collective",
+                "l2": "inputs (1 GiB per pass) exceed the 126 MB L2; no explicit flush",
+                "handle_type": int(info.handle_type),
+            },
+            "device_ms_globaltimer": device_ms,
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 2776,
+                    "d2h_bytes_per_step": 32 + 120 * int(res.phases),
+                    "note": "cdprobe_run from a host thread: kernel parameters (2776 B) in, result row "
+                            "(pinned host memory written by the kernel) out; the probe's inputs are "
+                            "generated on the device by design"},
+            "gpu_launches": args.steps * n,
+            "per_link_gbps": {
+                "read_min": min(pairs_r), "read_median": statistics.median(pairs_r), "read_max": max(pairs_r),
+                "write_min": min(pairs_w), "write_median": statistics.median(pairs_w), "write_max": max(pairs_w),
+                "peak": NVLINK_PEAK_GBPS if n > 1 else peaks["hbm_gbs"],
+                "frac_min": min(min(pairs_r), min(pairs_w)) / (NVLINK_PEAK_GBPS if n > 1 else peaks["hbm_gbs"]),
+                "run_to_run_spread_read": spread_r, "run_to_run_spread_write": spread_w,
+            },
+            "reachability_all_ones": reach_ok, "verdict": bool(res.verdict),
+            "roofline": roofline, "clocks": clocks,
+        }
+        if nvl0 and nvl1:
+            line["nvlink_counters"] = {
+                "tx_kib_delta": nvl1["tx_kib"] - nvl0["tx_kib"], "rx_kib_delta": nvl1["rx_kib"] - nvl0["rx_kib"],
+                "algorithmic_kib_per_direction": (2 * args.steps + 4) * a_gpu // 1024,
+                "note": "NVML field 138/139 on rank 0's GPU across both timed loops"}
+        if n == 1 and not args.no_cpu_baseline:
+            try:
+                times, last = cpu_poll_timing(1, 20, 2, budget_s=25.0)
+                line["cpu_baseline"] = {
+                    "value": statistics.mean(times), "unit": "ms", "cores": 1, "kind": "port",
+                    "host_cores": os.cpu_count(),
+                    "sample": (f"{len(times)} NVML polls of this node's {last.n} visible GPU(s) "
+                               f"({last.nvml_calls} NVML calls each: init, enumerate, fabric info, 18 NvLinkState "
+                               f"per GPU, P2PStatus per ordered pair, shutdown) = BASELINE configs[0]"),
+                    "median_ms": statistics.median(times)}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 1, "kind": "port",
+                                        "sample": f"unavailable: {e}"}
+        print(json.dumps(line))
+    probe.Close()
+    grp.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cdprobe", choices=["cdprobe", "reference"])
+    ap.add_argument("--bytes", type=int, default=GIB)
+    ap.add_argument("--mode", default="sliced", choices=["sliced", "full", "reach"])
+    ap.add_argument("--path", default="tma", choices=["tma", "ldst"])
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--timeout-ms", type=int, default=10000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_probe(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

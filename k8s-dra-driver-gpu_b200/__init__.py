@@ -11,7 +11,7 @@ The directory name contains hyphens (the layout the task prescribes); import it
 through ``cdprobe_pkg.load()`` at the repo root, which registers it as
 ``k8s_dra_driver_gpu_b200``.
 """
-from . import abi, build  # noqa: F401
+from . import abi, build, distutil  # noqa: F401
 from .fabricprobe import (  # noqa: F401
     Config,
     ErrUnsupported,

@@ -10,6 +10,7 @@
 // Every offset is 2 MiB granular (VMM granularity); slices/slots are 128 B
 // aligned.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -118,7 +119,8 @@ struct ProbeParams {
   uint32_t full_mode;              // source has a single slice
   Phase phase[kMaxPhases];
 };
-static_assert(sizeof(ProbeParams) <= 4000, "kernel parameter space");
+static_assert(sizeof(ProbeParams) == 2776, "kernel parameter bytes (bench.py reports them as h2d bytes per step)");
+static_assert(sizeof(PhaseOut) == 120 && offsetof(ResultRow, ph) == 32, "result row bytes (bench.py: d2h per step)");
 
 // ---- integer definitions shared with the oracle (oracle/pattern.c restates them) ----
 CDP_HD inline uint64_t splitmix64(uint64_t x) {
