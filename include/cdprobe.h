@@ -181,6 +181,7 @@ CDPROBE_API int cdprobe_info(cdprobe_t* h, cdprobe_info_t* out);
 #define CDPROBE_OPT_PATH 3u          /* 0 = TMA bulk copies, 1 = ld/st.global.v4 */
 #define CDPROBE_OPT_TIMEOUT_MS 4u
 #define CDPROBE_OPT_OVERLAP_VERIFY 5u /* value 0/1 */
+#define CDPROBE_OPT_VERIFY_CTAS 6u   /* CTAs given to the overlapped verify (default 32) */
 CDPROBE_API int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value);
 /* Storm/unprepare emulation: unmap + remap rank `peer` in local rank `local`'s address space. */
 CDPROBE_API int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer);

@@ -90,6 +90,7 @@ struct cdprobe {
   uint64_t src_xor[kMaxRanks][kMaxRanks] = {};
   bool sticky = false;
   bool event_timing = false;
+  uint32_t verify_ctas = 32;  // CTAs that verify landing slots under CDPROBE_FLAG_OVERLAP_VERIFY
   double open_ms = 0, fill_ms = 0;
 };
 
@@ -186,46 +187,89 @@ static bool pair_ok(const cdprobe* h, uint32_t a, uint32_t b) {
 }
 
 // Phase table of local rank li (SURVEY.md §8d schedule: rounds x {read, write}, then verify).
+// With CDPROBE_FLAG_OVERLAP_VERIFY the landing slot a partner filled in round r is verified by
+// the last `verify_ctas` CTAs while the other CTAs drive round r + 1 over NVLink: local HBM has
+// ~8x the bandwidth of the link, so the verify disappears from the critical path.
 static void build_phases(cdprobe* h, uint32_t li) {
   LocalRank& L = h->lr[li];
   const Plan& pl = h->plan;
   const uint32_t g = L.grank;
   const uint32_t ops = h->cfg.ops;
   uint32_t n = 0;
-  auto push = [&](uint8_t kind, int peer, uint32_t slot, uint32_t writer, bool sync_all) {
+  auto set_job = [&](Job& j, uint8_t kind, int peer, uint32_t slot, uint32_t writer, uint32_t cta0, uint32_t nctas) {
+    memset(&j, 0, sizeof(j));
+    j.kind = kind;
+    j.peer = (int8_t)peer;
+    j.slot = (uint8_t)slot;
+    j.writer = (uint8_t)writer;
+    j.cta0 = (uint16_t)cta0;
+    j.nctas = (uint16_t)nctas;
+  };
+  auto push = [&](uint8_t kind, int peer, uint32_t slot, uint32_t writer, bool sync_all) -> Phase& {
     Phase& p = L.phases[n++];
     memset(&p, 0, sizeof(p));
-    p.job[0].kind = kind;
-    p.job[0].peer = (int8_t)peer;
-    p.job[0].slot = (uint8_t)slot;
-    p.job[0].writer = (uint8_t)writer;
-    p.job[0].cta0 = 0;
-    p.job[0].nctas = (uint16_t)L.ctas;
+    set_job(p.job[0], kind, peer, slot, writer, 0, L.ctas);
     p.sync_all = sync_all ? 1u : 0u;
+    return p;
+  };
+  uint32_t vctas = h->verify_ctas;
+  const bool overlap = (h->cfg.flags & CDPROBE_FLAG_OVERLAP_VERIFY) && (ops & CDPROBE_OP_WRITE) && pl.rounds > 0 &&
+                       vctas > 0 && L.ctas >= 2 * vctas;
+  struct Pending {
+    bool have = false, ok = false;
+    uint32_t slot = 0, writer = 0;
+  } pend;
+  auto attach = [&](Phase& p) {  // give the tail CTAs of phase p the pending verify
+    if (!pend.have) return;
+    if (p.job[0].kind != kJobNone) p.job[0].nctas = (uint16_t)(L.ctas - vctas);
+    set_job(p.job[1], pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, L.ctas - vctas, vctas);
+    pend.have = false;
   };
   for (uint32_t r = 0; r < pl.rounds; ++r) {
     const int p = pl.partner[r][g];
     const bool ok = p >= 0 && pair_ok(h, g, (uint32_t)p);
     const uint32_t slot = ok ? slot_of(g, (uint32_t)p) : 0;
-    if (ops & CDPROBE_OP_READ) push(ok ? kJobRead : kJobNone, ok ? p : (int)g, slot, 0, true);
-    if (ops & CDPROBE_OP_WRITE) push(ok ? kJobWrite : kJobNone, ok ? p : (int)g, slot, 0, true);
+    if (ops & CDPROBE_OP_READ) {
+      Phase& ph = push(ok ? kJobRead : kJobNone, ok ? p : (int)g, slot, 0, true);
+      if (overlap) attach(ph);
+    }
+    if (ops & CDPROBE_OP_WRITE) {
+      Phase& ph = push(ok ? kJobWrite : kJobNone, ok ? p : (int)g, slot, 0, true);
+      if (overlap) {
+        attach(ph);
+        if (p >= 0) {  // what the partner stores into my landing area during this phase
+          pend.have = true;
+          pend.ok = ok;
+          pend.slot = slot_of((uint32_t)p, g);
+          pend.writer = (uint32_t)p;
+        }
+      }
+    }
   }
   if (pl.diag) {
     if (ops & CDPROBE_OP_READ) push(kJobRead, (int)g, pl.diag_slot, 0, false);
     if (ops & CDPROBE_OP_WRITE) push(kJobWrite, (int)g, pl.diag_slot, 0, false);
   }
   if (ops & CDPROBE_OP_WRITE) {
-    for (uint32_t s = 0; s < pl.n_slots; ++s) {
-      uint32_t writer;
-      bool ok;
-      if (pl.diag && s == pl.diag_slot) {
-        writer = g;
-        ok = true;
-      } else {
-        writer = s < g ? s : s + 1;
-        ok = pair_ok(h, g, writer);
+    if (overlap) {
+      // always present (a rank that sat out the last round of an odd-sized domain pushes an idle
+      // phase) so that every rank has the same number of barriers
+      push(pend.have && pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, false);
+      pend.have = false;
+      if (pl.diag) push(kJobVerify, (int)g, pl.diag_slot, g, false);
+    } else {
+      for (uint32_t s = 0; s < pl.n_slots; ++s) {
+        uint32_t writer;
+        bool ok;
+        if (pl.diag && s == pl.diag_slot) {
+          writer = g;
+          ok = true;
+        } else {
+          writer = s < g ? s : s + 1;
+          ok = pair_ok(h, g, writer);
+        }
+        push(ok ? kJobVerify : kJobNone, (int)g, s, writer, false);
       }
-      push(ok ? kJobVerify : kJobNone, (int)g, s, writer, false);
     }
   }
   if (n > 0) L.phases[n - 1].sync_all = 1u;  // verdicts must be visible before the rows are written
@@ -896,6 +940,11 @@ int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
       return CDPROBE_OK;
     case CDPROBE_OPT_OVERLAP_VERIFY:
       h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_OVERLAP_VERIFY) | (value ? CDPROBE_FLAG_OVERLAP_VERIFY : 0u);
+      for (uint32_t li = 0; li < h->n_local; ++li) cdp::build_phases(h, li);
+      return CDPROBE_OK;
+    case CDPROBE_OPT_VERIFY_CTAS:
+      if (value == 0 || value > 65535) return CDPROBE_ERR_ARG;
+      h->verify_ctas = (uint32_t)value;
       for (uint32_t li = 0; li < h->n_local; ++li) cdp::build_phases(h, li);
       return CDPROBE_OK;
     default:
