@@ -272,6 +272,23 @@ def run_probe(args):
     spread_r = max_over_ranks(spread_r or 0.0)
     spread_w = max_over_ranks(spread_w or 0.0)
 
+    # per-link figure with one-way payload (each ordered pair alone on its two ports): a few extra,
+    # untimed-for-the-headline runs with the unidirectional schedule
+    uni = None
+    if n > 1:
+        probe.SetOption(abi.OPT_UNIDIRECTIONAL, 1)
+        for _ in range(2):
+            probe.Run()
+        ur = [probe.Run(gather=True) for _ in range(3)]
+        probe.SetOption(abi.OPT_UNIDIRECTIONAL, 0)
+        u_r = [statistics.median(u.gbps_read[i][j] for u in ur) for i in range(n) for j in range(n) if i != j]
+        u_w = [statistics.median(u.gbps_write[i][j] for u in ur) for i in range(n) for j in range(n) if i != j]
+        uni = {"read_min": min(u_r), "read_median": statistics.median(u_r), "write_min": min(u_w),
+               "write_median": statistics.median(u_w), "probe_ms": statistics.median(u.probe_ms for u in ur),
+               "frac_min_of_900": min(min(u_r), min(u_w)) / NVLINK_PEAK_GBPS,
+               "frac_min_of_measured_770": min(min(u_r), min(u_w)) / NVLINK_MEASURED_GBPS,
+               "reach_all_ones": all(all(all(c == 1 for c in row) for row in u.reach) for u in ur)}
+
     peaks, peak_kind = measured_peaks()
     passes = 3  # read B, write B, verify B per GPU per probe
     a_gpu = (n - 1 if n > 1 else 1) * bpp
@@ -327,21 +344,26 @@ def run_probe(args):
             "reachability_all_ones": reach_ok, "verdict": bool(res.verdict),
             "roofline": roofline, "clocks": clocks,
         }
+        if uni is not None:
+            line["per_link_gbps_unidirectional"] = uni
         if nvl0 and nvl1:
             line["nvlink_counters"] = {
                 "tx_kib_delta": nvl1["tx_kib"] - nvl0["tx_kib"], "rx_kib_delta": nvl1["rx_kib"] - nvl0["rx_kib"],
                 "algorithmic_kib_per_direction": (2 * args.steps + 4) * a_gpu // 1024,
                 "note": "NVML field 138/139 on rank 0's GPU across both timed loops"}
         if n == 1 and not args.no_cpu_baseline:
+            # fresh process, as the reference's `check` is exec'ed per kubelet probe (NVML init is not
+            # amortised): the reference arm of this same script, bounded to ~20 polls
             try:
-                times, last = cpu_poll_timing(1, 20, 2, budget_s=25.0)
-                line["cpu_baseline"] = {
-                    "value": statistics.mean(times), "unit": "ms", "cores": 1, "kind": "port",
-                    "host_cores": os.cpu_count(),
-                    "sample": (f"{len(times)} NVML polls of this node's {last.n} visible GPU(s) "
-                               f"({last.nvml_calls} NVML calls each: init, enumerate, fabric info, 18 NvLinkState "
-                               f"per GPU, P2PStatus per ordered pair, shutdown) = BASELINE configs[0]"),
-                    "median_ms": statistics.median(times)}
+                import subprocess
+
+                env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+                cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1",
+                                     "--steps", "20", "--warmup", "2"], capture_output=True, text=True, timeout=120,
+                                    env=env)
+                ref = json.loads([l for l in cp.stdout.splitlines() if l.startswith("{")][-1])
+                line["cpu_baseline"] = ref.get("cpu_baseline") or {"value": None, "unit": "ms", "cores": 1,
+                                                                     "kind": "port", "sample": ref.get("unavailable")}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 1, "kind": "port",
                                         "sample": f"unavailable: {e}"}

@@ -75,6 +75,8 @@ extern "C" {
 #define CDPROBE_FLAG_NO_COOPERATIVE 0x10u  /* plain launch (tests that put 2 ranks on one device) */
 #define CDPROBE_FLAG_OVERLAP_VERIFY 0x20u  /* verify landing slots on spare CTAs while the next round runs */
 #define CDPROBE_FLAG_ALLOW_SAME_DEVICE 0x40u /* several ranks may name the same CUDA ordinal (testing) */
+#define CDPROBE_FLAG_UNIDIRECTIONAL 0x80u  /* each round in two halves: one rank of a pair issues at a time, so a
+                                              port carries payload one way only (per-link figure; 2x the phases) */
 
 typedef struct cdprobe cdprobe_t;
 
@@ -182,6 +184,7 @@ CDPROBE_API int cdprobe_info(cdprobe_t* h, cdprobe_info_t* out);
 #define CDPROBE_OPT_TIMEOUT_MS 4u
 #define CDPROBE_OPT_OVERLAP_VERIFY 5u /* value 0/1 */
 #define CDPROBE_OPT_VERIFY_CTAS 6u   /* CTAs given to the overlapped verify (default 32) */
+#define CDPROBE_OPT_UNIDIRECTIONAL 7u /* value 0/1: see CDPROBE_FLAG_UNIDIRECTIONAL */
 CDPROBE_API int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value);
 /* Storm/unprepare emulation: unmap + remap rank `peer` in local rank `local`'s address space. */
 CDPROBE_API int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer);

@@ -21,8 +21,10 @@ FLAG_PATH_LDST = 0x08
 FLAG_NO_COOPERATIVE = 0x10
 FLAG_OVERLAP_VERIFY = 0x20
 FLAG_ALLOW_SAME_DEVICE = 0x40
+FLAG_UNIDIRECTIONAL = 0x80
 
 OPT_EVENT_TIMING, OPT_CTAS, OPT_PATH, OPT_TIMEOUT_MS, OPT_OVERLAP_VERIFY, OPT_VERIFY_CTAS = 1, 2, 3, 4, 5, 6
+OPT_UNIDIRECTIONAL = 7
 
 _N2 = MAX_GPUS * MAX_GPUS
 

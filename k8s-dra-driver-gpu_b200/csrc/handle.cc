@@ -190,7 +190,7 @@ static bool pair_ok(const cdprobe* h, uint32_t a, uint32_t b) {
 // With CDPROBE_FLAG_OVERLAP_VERIFY the landing slot a partner filled in round r is verified by
 // the last `verify_ctas` CTAs while the other CTAs drive round r + 1 over NVLink: local HBM has
 // ~8x the bandwidth of the link, so the verify disappears from the critical path.
-static void build_phases(cdprobe* h, uint32_t li) {
+static int build_phases(cdprobe* h, uint32_t li) {
   LocalRank& L = h->lr[li];
   const Plan& pl = h->plan;
   const uint32_t g = L.grank;
@@ -205,7 +205,13 @@ static void build_phases(cdprobe* h, uint32_t li) {
     j.cta0 = (uint16_t)cta0;
     j.nctas = (uint16_t)nctas;
   };
+  bool overflow = false;
+  Phase scratch;
   auto push = [&](uint8_t kind, int peer, uint32_t slot, uint32_t writer, bool sync_all) -> Phase& {
+    if (n >= (uint32_t)kMaxPhases) {
+      overflow = true;
+      return scratch;
+    }
     Phase& p = L.phases[n++];
     memset(&p, 0, sizeof(p));
     set_job(p.job[0], kind, peer, slot, writer, 0, L.ctas);
@@ -225,23 +231,33 @@ static void build_phases(cdprobe* h, uint32_t li) {
     set_job(p.job[1], pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, L.ctas - vctas, vctas);
     pend.have = false;
   };
+  // Bidirectional (default): both ranks of a pair issue at once, so every NVLink port carries
+  // data in both directions.  CDPROBE_FLAG_UNIDIRECTIONAL splits a round in two halves — the
+  // lower rank of the pair issues first, then the higher — so each ordered pair is measured
+  // with its two ports carrying payload one way only (the classic per-link figure).
+  const bool uni = (h->cfg.flags & CDPROBE_FLAG_UNIDIRECTIONAL) != 0;
   for (uint32_t r = 0; r < pl.rounds; ++r) {
     const int p = pl.partner[r][g];
     const bool ok = p >= 0 && pair_ok(h, g, (uint32_t)p);
     const uint32_t slot = ok ? slot_of(g, (uint32_t)p) : 0;
-    if (ops & CDPROBE_OP_READ) {
-      Phase& ph = push(ok ? kJobRead : kJobNone, ok ? p : (int)g, slot, 0, true);
-      if (overlap) attach(ph);
-    }
-    if (ops & CDPROBE_OP_WRITE) {
-      Phase& ph = push(ok ? kJobWrite : kJobNone, ok ? p : (int)g, slot, 0, true);
-      if (overlap) {
-        attach(ph);
-        if (p >= 0) {  // what the partner stores into my landing area during this phase
-          pend.have = true;
-          pend.ok = ok;
-          pend.slot = slot_of((uint32_t)p, g);
-          pend.writer = (uint32_t)p;
+    for (int half = 0; half < (uni ? 2 : 1); ++half) {
+      const bool i_active = !uni || ((half == 0) == ((int)g < p));
+      const bool p_active = !uni || !i_active;
+      const bool mine = ok && i_active;
+      if (ops & CDPROBE_OP_READ) {
+        Phase& ph = push(mine ? kJobRead : kJobNone, mine ? p : (int)g, slot, 0, true);
+        if (overlap) attach(ph);
+      }
+      if (ops & CDPROBE_OP_WRITE) {
+        Phase& ph = push(mine ? kJobWrite : kJobNone, mine ? p : (int)g, slot, 0, true);
+        if (overlap) {
+          attach(ph);
+          if (p >= 0 && p_active) {  // what the partner stores into my landing area during this phase
+            pend.have = true;
+            pend.ok = ok;
+            pend.slot = slot_of((uint32_t)p, g);
+            pend.writer = (uint32_t)p;
+          }
         }
       }
     }
@@ -272,12 +288,26 @@ static void build_phases(cdprobe* h, uint32_t li) {
       }
     }
   }
+  if (overflow) {
+    set_err("schedule needs more than CDPROBE_MAX_PHASES phases (use overlap-verify or fewer ops)");
+    L.n_phases = 0;
+    return CDPROBE_ERR_ARG;
+  }
   if (n > 0) L.phases[n - 1].sync_all = 1u;  // verdicts must be visible before the rows are written
   L.n_phases = n;
   uint32_t mask = 0;
   for (uint32_t j = 0; j < h->n_total; ++j)
     if (j != g && pair_ok(h, g, j)) mask |= 1u << j;
   L.peer_mask = mask;
+  return CDPROBE_OK;
+}
+
+static int rebuild_all(cdprobe* h) {
+  for (uint32_t li = 0; li < h->n_local; ++li) {
+    const int rc = build_phases(h, li);
+    if (rc != CDPROBE_OK) return rc;
+  }
+  return CDPROBE_OK;
 }
 
 static void fill_params(const cdprobe* h, uint32_t li, const Phase* phases, uint32_t n_phases, uint32_t peer_mask,
@@ -659,7 +689,8 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
     const int32_t* flat = &all[0][0][0];
     for (uint32_t g = 0; g < h->n_total; ++g) memcpy(h->status[g], flat + (size_t)g * kMaxRanks, sizeof(h->status[g]));
   }
-  for (uint32_t li = 0; li < h->n_local; ++li) build_phases(h, li);
+  rc = rebuild_all(h);
+  if (rc != CDPROBE_OK) return rc;
   h->open_ms = now_ms() - t0;
 
   const double t1 = now_ms();
@@ -927,9 +958,8 @@ int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
         uint32_t c = value ? (uint32_t)value : (uint32_t)L.sm_count;
         if (c > (uint32_t)L.max_ctas) c = (uint32_t)L.max_ctas;
         L.ctas = c;
-        cdp::build_phases(h, li);
       }
-      return CDPROBE_OK;
+      return cdp::rebuild_all(h);
     case CDPROBE_OPT_PATH:
       if (value > 1) return CDPROBE_ERR_ARG;
       h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_PATH_LDST) | (value ? CDPROBE_FLAG_PATH_LDST : 0u);
@@ -939,14 +969,31 @@ int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
       h->cfg.timeout_ms = (uint32_t)value;
       return CDPROBE_OK;
     case CDPROBE_OPT_OVERLAP_VERIFY:
+    {
+      const uint32_t old = h->cfg.flags;
       h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_OVERLAP_VERIFY) | (value ? CDPROBE_FLAG_OVERLAP_VERIFY : 0u);
-      for (uint32_t li = 0; li < h->n_local; ++li) cdp::build_phases(h, li);
-      return CDPROBE_OK;
+      const int rc = cdp::rebuild_all(h);
+      if (rc != CDPROBE_OK) {
+        h->cfg.flags = old;
+        cdp::rebuild_all(h);
+      }
+      return rc;
+    }
+    case CDPROBE_OPT_UNIDIRECTIONAL:
+    {
+      const uint32_t old = h->cfg.flags;
+      h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_UNIDIRECTIONAL) | (value ? CDPROBE_FLAG_UNIDIRECTIONAL : 0u);
+      const int rc = cdp::rebuild_all(h);
+      if (rc != CDPROBE_OK) {
+        h->cfg.flags = old;
+        cdp::rebuild_all(h);
+      }
+      return rc;
+    }
     case CDPROBE_OPT_VERIFY_CTAS:
       if (value == 0 || value > 65535) return CDPROBE_ERR_ARG;
       h->verify_ctas = (uint32_t)value;
-      for (uint32_t li = 0; li < h->n_local; ++li) cdp::build_phases(h, li);
-      return CDPROBE_OK;
+      return cdp::rebuild_all(h);
     default:
       return CDPROBE_ERR_ARG;
   }
@@ -959,8 +1006,7 @@ int cdprobe_unmap_peer(cdprobe_t* h, uint32_t local, uint32_t peer) {
   if (peer == g) return CDPROBE_ERR_ARG;
   cdp::unmap_peer(h, local, peer);
   h->status[g][peer] = cdp::kStatusUnmapped;
-  for (uint32_t li = 0; li < h->n_local; ++li) cdp::build_phases(h, li);
-  return CDPROBE_OK;
+  return cdp::rebuild_all(h);
 }
 
 int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer) {
@@ -970,7 +1016,8 @@ int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer) {
   if (peer == g) return CDPROBE_ERR_ARG;
   cdp::unmap_peer(h, local, peer);
   h->status[g][peer] = cdp::map_peer(h, local, peer);
-  for (uint32_t li = 0; li < h->n_local; ++li) cdp::build_phases(h, li);
+  const int rc = cdp::rebuild_all(h);
+  if (rc != CDPROBE_OK) return rc;
   return h->status[g][peer] == 0 ? CDPROBE_OK : CDPROBE_ERR_CUDA;
 }
 

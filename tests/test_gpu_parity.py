@@ -134,6 +134,38 @@ def test_same_device_ranks(pkg, oracle, n, mode, path_flag):
             assert r.rounds == (n if n % 2 else n - 1)
 
 
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("flags", [0x80, 0x20, 0xA0], ids=["unidirectional", "overlap-verify", "uni+overlap"])
+def test_schedule_variants_keep_parity(pkg, oracle, n, flags):
+    """Unidirectional half-rounds and the overlapped verify only reorder phases: every checksum
+    and reachability bit must be unchanged."""
+    nbytes = 2 << 20
+    cfg = pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME | flags, ctas=8, timeout_ms=20000)
+    with pkg.Open(cfg) as p:
+        p.SetOption(pkg.abi.OPT_VERIFY_CTAS, 3)
+        for _ in range(2):
+            r = p.Run()
+            assert not r.aborted and r.row_mask == (1 << n) - 1
+            check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+            assert r.reach == [[1] * n for _ in range(n)]
+
+
+def test_runtime_options_round_trip(pkg, oracle):
+    n, nbytes = 4, 1 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
+        base = p.Run()
+        for opt, val in ((pkg.abi.OPT_PATH, 1), (pkg.abi.OPT_UNIDIRECTIONAL, 1), (pkg.abi.OPT_OVERLAP_VERIFY, 1),
+                         (pkg.abi.OPT_VERIFY_CTAS, 2), (pkg.abi.OPT_CTAS, 6), (pkg.abi.OPT_EVENT_TIMING, 1),
+                         (pkg.abi.OPT_PATH, 0), (pkg.abi.OPT_UNIDIRECTIONAL, 0), (pkg.abi.OPT_OVERLAP_VERIFY, 0)):
+            p.SetOption(opt, val)
+            r = p.Run()
+            assert r.sum_read == base.sum_read and r.xor_read == base.xor_read
+            check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+        assert max(r.event_ms) > 0
+        with pytest.raises(pkg.ProbeError):
+            p.SetOption(99, 1)
+
+
 def test_same_device_with_diagonal(pkg, oracle):
     n, nbytes = 4, 1 << 20
     cfg = pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME | pkg.abi.FLAG_LOCAL_DIAG, ctas=8, timeout_ms=20000)

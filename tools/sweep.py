@@ -21,6 +21,9 @@ ap.add_argument("--ctas", default="148,128,96,74,64,48,32")
 ap.add_argument("--iters", type=int, default=8)
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
 ap.add_argument("--overlap", default="0")
+ap.add_argument("--uni", default="0")
+ap.add_argument("--paths", default="0,1")
+ap.add_argument("--vctas", type=int, default=32)
 args = ap.parse_args()
 
 mode = {"sliced": 1, "full": 2, "reach": 0}[args.mode]
@@ -28,9 +31,11 @@ n = args.gpus
 os.makedirs(os.path.dirname(args.out), exist_ok=True)
 with pkg.Open(pkg.Config(ordinals=list(range(n)), bytes=args.bytes, mode=mode, timeout_ms=20000)) as p, open(args.out, "a") as f:
     p.SetOption(abi.OPT_EVENT_TIMING, 1)
-    for overlap in [int(x) for x in args.overlap.split(",")]:
+    p.SetOption(abi.OPT_VERIFY_CTAS, args.vctas)
+    for uni, overlap in [(int(u), int(x)) for u in args.uni.split(",") for x in args.overlap.split(",")]:
+        p.SetOption(abi.OPT_UNIDIRECTIONAL, uni)
         p.SetOption(abi.OPT_OVERLAP_VERIFY, overlap)
-        for path in (0, 1):
+        for path in [int(x) for x in args.paths.split(",")]:
             p.SetOption(abi.OPT_PATH, path)
             for ctas in [int(c) for c in args.ctas.split(",")]:
                 p.SetOption(abi.OPT_CTAS, ctas)
@@ -40,7 +45,7 @@ with pkg.Open(pkg.Config(ordinals=list(range(n)), bytes=args.bytes, mode=mode, t
                 off = [(i, j) for i in range(n) for j in range(n) if i != j or n == 1]
                 rec = {
                     "n": n, "mode": args.mode, "bytes": args.bytes, "path": "ldst" if path else "tma", "ctas": ctas,
-                    "overlap": overlap, "bpp": rs[0].bytes_per_pair, "phases": rs[0].phases,
+                    "overlap": overlap, "uni": uni, "bpp": rs[0].bytes_per_pair, "phases": rs[0].phases,
                     "probe_ms": statistics.median(r.probe_ms for r in rs),
                     "probe_ms_min": min(r.probe_ms for r in rs),
                     "event_ms": statistics.median(max(r.event_ms) for r in rs),
