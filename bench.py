@@ -49,7 +49,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.01):
+    def __init__(self, index: int, period_s: float = 0.025):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -267,10 +267,17 @@ def run_probe(args):
     pairs_r = [res.gbps_read[i][j] for i in range(n) for j in range(n) if i != j or n == 1]
     pairs_w = [res.gbps_write[i][j] for i in range(n) for j in range(n) if i != j or n == 1]
     reach_ok = all(res.reach[i][j] == 1 for i in range(n) for j in range(n))
-    spread_r = (max(rd) - min(rd)) / statistics.median(rd) if rd and statistics.median(rd) > 0 else None
-    spread_w = (max(wr) - min(wr)) / statistics.median(wr) if wr and statistics.median(wr) > 0 else None
-    spread_r = max_over_ranks(spread_r or 0.0)
-    spread_w = max_over_ranks(spread_w or 0.0)
+    def pct(v, f):
+        v = sorted(v)
+        return v[min(len(v) - 1, max(0, int(round(f * (len(v) - 1)))))]
+
+    # run-to-run repeatability of this rank's slowest pair: central 90 % spread (p95 - p5) / median, and
+    # the worst single step; max over ranks
+    spread_r = max_over_ranks((pct(rd, 0.95) - pct(rd, 0.05)) / statistics.median(rd))
+    spread_w = max_over_ranks((pct(wr, 0.95) - pct(wr, 0.05)) / statistics.median(wr))
+    worst_r = max_over_ranks((statistics.median(rd) - min(rd)) / statistics.median(rd))
+    worst_w = max_over_ranks((statistics.median(wr) - min(wr)) / statistics.median(wr))
+    ev_spread = max_over_ranks((max(ev) - min(ev)) / statistics.median(ev))
 
     # per-link figure with one-way payload (each ordered pair alone on its two ports): a few extra,
     # untimed-for-the-headline runs with the unidirectional schedule
@@ -340,6 +347,7 @@ def run_probe(args):
                 "peak": NVLINK_PEAK_GBPS if n > 1 else peaks["hbm_gbs"],
                 "frac_min": min(min(pairs_r), min(pairs_w)) / (NVLINK_PEAK_GBPS if n > 1 else peaks["hbm_gbs"]),
                 "run_to_run_spread_read": spread_r, "run_to_run_spread_write": spread_w,
+                "worst_step_drop_read": worst_r, "worst_step_drop_write": worst_w, "probe_ms_spread": ev_spread,
             },
             "reachability_all_ones": reach_ok, "verdict": bool(res.verdict),
             "roofline": roofline, "clocks": clocks,
