@@ -73,7 +73,8 @@ extern "C" {
 #define CDPROBE_FLAG_LOCAL_DIAG 0x04u      /* also measure the diagonal (loop-back into local HBM; always on when n == 1) */
 #define CDPROBE_FLAG_PATH_LDST 0x08u       /* 128-bit ld/st.global instead of TMA bulk copies */
 #define CDPROBE_FLAG_NO_COOPERATIVE 0x10u  /* plain launch (tests that put 2 ranks on one device) */
-#define CDPROBE_FLAG_OVERLAP_VERIFY 0x20u  /* verify landing slots on spare CTAs while the next round runs */
+#define CDPROBE_FLAG_OVERLAP_VERIFY 0x20u  /* verify landing slots on spare CTAs while the next round runs (default) */
+#define CDPROBE_FLAG_SERIAL_VERIFY 0x100u  /* opt out of the overlapped verify: verify every slot after the rounds */
 #define CDPROBE_FLAG_ALLOW_SAME_DEVICE 0x40u /* several ranks may name the same CUDA ordinal (testing) */
 #define CDPROBE_FLAG_UNIDIRECTIONAL 0x80u  /* each round in two halves: one rank of a pair issues at a time, so a
                                               port carries payload one way only (per-link figure; 2x the phases) */
@@ -167,6 +168,31 @@ typedef struct {
   int8_t partner[CDPROBE_MAX_GPUS][CDPROBE_MAX_GPUS]; /* [round][rank], -1 = idle */
 } cdprobe_plan_t;
 
+/* Per-phase timeline of the last run of one local rank (ns, relative to the first barrier release). */
+typedef struct {
+  uint32_t abi;
+  uint32_t n_phases;
+  uint8_t kind0[CDPROBE_MAX_PHASES], kind1[CDPROBE_MAX_PHASES];  /* 0 none, 1 read, 2 write, 3 verify */
+  int8_t peer0[CDPROBE_MAX_PHASES], peer1[CDPROBE_MAX_PHASES];
+  uint8_t sync_all[CDPROBE_MAX_PHASES];                          /* closing barrier spans all ranks */
+  uint64_t t_start[CDPROBE_MAX_PHASES];                          /* opening barrier released */
+  uint64_t t_end0[CDPROBE_MAX_PHASES], t_end1[CDPROBE_MAX_PHASES]; /* last CTA of job 0 / job 1 done */
+  uint64_t t_arrive[CDPROBE_MAX_PHASES];                         /* every local CTA reached the closing barrier */
+} cdprobe_trace_t;
+
+/* Node topology as NVML reports it (no CUDA; internal/common topology enumeration). */
+typedef struct {
+  uint32_t abi;
+  uint32_t n;                                     /* GPUs NVML enumerates, in NVML index order */
+  char uuid[CDPROBE_MAX_GPUS][96];                /* nvmlDeviceGetUUID */
+  char pci_bus_id[CDPROBE_MAX_GPUS][32];
+  uint8_t mig[CDPROBE_MAX_GPUS];                  /* MIG mode currently enabled */
+  uint8_t links_active[CDPROBE_MAX_GPUS];         /* NvLinkState == ENABLED over the 18 links */
+  uint8_t fabric_state[CDPROBE_MAX_GPUS];         /* nvmlGpuFabricInfo_t.state */
+  char clique_id[96];                             /* "<clusterUUID>.<cliqueId>" or "" (nvlib.go:208-363) */
+  char clique_error[160];                         /* non-empty: getCliqueID would return this error */
+} cdprobe_topology_t;
+
 CDPROBE_API uint32_t cdprobe_abi_version(void);
 CDPROBE_API const char* cdprobe_strerror(int code);
 /* Detail of the last failure on the calling thread ("cuMemMap: CUDA_ERROR_..."), "" if none. */
@@ -177,6 +203,7 @@ CDPROBE_API int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out);
 /* Collective over all processes of the domain: completes rows of other processes. No-op for world_size <= 1. */
 CDPROBE_API int cdprobe_gather(cdprobe_t* h, cdprobe_result_t* inout);
 CDPROBE_API int cdprobe_info(cdprobe_t* h, cdprobe_info_t* out);
+CDPROBE_API int cdprobe_trace(cdprobe_t* h, uint32_t local, cdprobe_trace_t* out);
 /* Runtime options (no reopen needed; the bench sweeps them). */
 #define CDPROBE_OPT_EVENT_TIMING 1u  /* value 0/1: bracket each kernel with CUDA events, report event_ms */
 #define CDPROBE_OPT_CTAS 2u          /* CTAs of the persistent kernel (0 = one per SM) */
@@ -196,6 +223,8 @@ CDPROBE_API void cdprobe_close(cdprobe_t* h);
 
 /* Host-only helpers (no CUDA): schedule + slice arithmetic; the fd/blob rendezvous self-test. */
 CDPROBE_API int cdprobe_plan(uint32_t n, uint64_t bytes, uint32_t mode, uint32_t flags, cdprobe_plan_t* out);
+/* strict != 0: getCliqueIDStrict (feature gate CrashOnNVLinkFabricErrors, default on), else the legacy walk. */
+CDPROBE_API int cdprobe_topology(uint32_t strict, cdprobe_topology_t* out);
 CDPROBE_API int cdprobe_rendezvous_selftest(const char* session, uint32_t rank, uint32_t world, uint32_t timeout_ms);
 
 #ifdef __cplusplus

@@ -20,6 +20,7 @@ from .fabricprobe import (  # noqa: F401
     Result,
     Open,
     plan,
+    topology,
 )
 
-__all__ = ["abi", "build", "Config", "Probe", "ProbeError", "ErrUnsupported", "Result", "Open", "plan"]
+__all__ = ["abi", "build", "Config", "Probe", "ProbeError", "ErrUnsupported", "Result", "Open", "plan", "topology"]

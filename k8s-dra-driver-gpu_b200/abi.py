@@ -22,6 +22,7 @@ FLAG_NO_COOPERATIVE = 0x10
 FLAG_OVERLAP_VERIFY = 0x20
 FLAG_ALLOW_SAME_DEVICE = 0x40
 FLAG_UNIDIRECTIONAL = 0x80
+FLAG_SERIAL_VERIFY = 0x100
 
 OPT_EVENT_TIMING, OPT_CTAS, OPT_PATH, OPT_TIMEOUT_MS, OPT_OVERLAP_VERIFY, OPT_VERIFY_CTAS = 1, 2, 3, 4, 5, 6
 OPT_UNIDIRECTIONAL = 7
@@ -119,6 +120,36 @@ class PlanT(C.Structure):
     ]
 
 
+class TraceT(C.Structure):
+    _fields_ = [
+        ("abi", C.c_uint32),
+        ("n_phases", C.c_uint32),
+        ("kind0", C.c_uint8 * MAX_PHASES),
+        ("kind1", C.c_uint8 * MAX_PHASES),
+        ("peer0", C.c_int8 * MAX_PHASES),
+        ("peer1", C.c_int8 * MAX_PHASES),
+        ("sync_all", C.c_uint8 * MAX_PHASES),
+        ("t_start", C.c_uint64 * MAX_PHASES),
+        ("t_end0", C.c_uint64 * MAX_PHASES),
+        ("t_end1", C.c_uint64 * MAX_PHASES),
+        ("t_arrive", C.c_uint64 * MAX_PHASES),
+    ]
+
+
+class TopologyT(C.Structure):
+    _fields_ = [
+        ("abi", C.c_uint32),
+        ("n", C.c_uint32),
+        ("uuid", (C.c_char * 96) * MAX_GPUS),
+        ("pci_bus_id", (C.c_char * 32) * MAX_GPUS),
+        ("mig", C.c_uint8 * MAX_GPUS),
+        ("links_active", C.c_uint8 * MAX_GPUS),
+        ("fabric_state", C.c_uint8 * MAX_GPUS),
+        ("clique_id", C.c_char * 96),
+        ("clique_error", C.c_char * 160),
+    ]
+
+
 # Every symbol include/cdprobe.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "cdprobe_abi_version": (C.c_uint32, []),
@@ -128,12 +159,14 @@ SYMBOLS = {
     "cdprobe_run": (C.c_int, [C.c_void_p, C.POINTER(ResultT)]),
     "cdprobe_gather": (C.c_int, [C.c_void_p, C.POINTER(ResultT)]),
     "cdprobe_info": (C.c_int, [C.c_void_p, C.POINTER(InfoT)]),
+    "cdprobe_trace": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TraceT)]),
     "cdprobe_set_option": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
     "cdprobe_remap_peer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cdprobe_unmap_peer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cdprobe_corrupt": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]),
     "cdprobe_close": (None, [C.c_void_p]),
     "cdprobe_plan": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(PlanT)]),
+    "cdprobe_topology": (C.c_int, [C.c_uint32, C.POINTER(TopologyT)]),
     "cdprobe_rendezvous_selftest": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32]),
 }
 

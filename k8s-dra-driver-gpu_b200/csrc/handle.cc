@@ -485,6 +485,7 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
   if (c.link_peak_gbps <= 0.f) c.link_peak_gbps = 900.f;
   if (c.world_size == 0) c.world_size = 1;
   if (c.rank >= c.world_size) return CDPROBE_ERR_ARG;
+  if (!(c.flags & CDPROBE_FLAG_SERIAL_VERIFY)) c.flags |= CDPROBE_FLAG_OVERLAP_VERIFY;  // overlapped verify is the default
   h->seed = c.seed ? c.seed : kDefaultSeed;
   c.session[sizeof(c.session) - 1] = '\0';
   memset(h->status, 0, sizeof(h->status));
@@ -943,6 +944,30 @@ int cdprobe_info(cdprobe_t* h, cdprobe_info_t* out) {
   out->smem_bytes = cdp::kSmemBytes;
   out->open_ms = h->open_ms;
   out->fill_ms = h->fill_ms;
+  return CDPROBE_OK;
+}
+
+int cdprobe_trace(cdprobe_t* h, uint32_t local, cdprobe_trace_t* out) {
+  if (h == nullptr || out == nullptr || local >= h->n_local) return CDPROBE_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  out->abi = CDPROBE_ABI_VERSION;
+  const cdp::LocalRank& L = h->lr[local];
+  const cdp::ResultRow* row = L.row;
+  out->n_phases = L.n_phases;
+  const uint64_t t0 = row->t_first;
+  auto rel = [&](uint64_t t) { return t > t0 ? t - t0 : 0ull; };
+  for (uint32_t p = 0; p < L.n_phases; ++p) {
+    const cdp::PhaseOut& o = row->ph[p];
+    out->kind0[p] = L.phases[p].job[0].kind;
+    out->kind1[p] = L.phases[p].job[1].kind;
+    out->peer0[p] = L.phases[p].job[0].peer;
+    out->peer1[p] = L.phases[p].job[1].peer;
+    out->sync_all[p] = (uint8_t)L.phases[p].sync_all;
+    out->t_start[p] = rel(o.t_start);
+    out->t_end0[p] = rel(o.t_end[0]);
+    out->t_end1[p] = rel(o.t_end[1]);
+    out->t_arrive[p] = rel(o.t_arrive);
+  }
   return CDPROBE_OK;
 }
 

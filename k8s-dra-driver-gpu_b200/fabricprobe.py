@@ -186,6 +186,17 @@ class Probe:
             _raise(self._lib, rc, "cdprobe_info")
         return i
 
+    def Trace(self, local: int = 0):
+        """Per-phase timeline of the last run: list of dicts (ns relative to the first barrier release)."""
+        t = abi.TraceT()
+        rc = self._lib.cdprobe_trace(self._h, local, C.byref(t))
+        if rc != abi.OK:
+            _raise(self._lib, rc, "cdprobe_trace")
+        names = {0: "-", 1: "read", 2: "write", 3: "verify"}
+        return [{"job0": names[t.kind0[p]], "peer0": t.peer0[p], "job1": names[t.kind1[p]], "peer1": t.peer1[p],
+                 "sync_all": int(t.sync_all[p]), "t_start": t.t_start[p], "t_end0": t.t_end0[p], "t_end1": t.t_end1[p],
+                 "t_arrive": t.t_arrive[p]} for p in range(t.n_phases)]
+
     def SetOption(self, option: int, value: int) -> None:
         rc = self._lib.cdprobe_set_option(self._h, option, value)
         if rc != abi.OK:
@@ -226,6 +237,16 @@ class Probe:
 
 def Open(cfg: Config) -> Probe:
     return Probe(cfg)
+
+
+def topology(strict: bool = True) -> abi.TopologyT:
+    """internal/common topology enumeration (NVML only, no CUDA)."""
+    lib = abi.load_library()
+    t = abi.TopologyT()
+    rc = lib.cdprobe_topology(1 if strict else 0, C.byref(t))
+    if rc != abi.OK:
+        _raise(lib, rc, "cdprobe_topology")
+    return t
 
 
 def plan(n: int, nbytes: int, mode: int, flags: int = 0) -> abi.PlanT:

@@ -41,7 +41,8 @@ def test_struct_layout_matches_c(pkg, tmp_path):
     """sizeof/offsetof of every ABI struct, taken from the header by gcc, equal the ctypes mirror."""
     a = pkg.abi
     structs = {"cdprobe_config_t": a.ConfigT, "cdprobe_result_t": a.ResultT, "cdprobe_info_t": a.InfoT,
-               "cdprobe_plan_t": a.PlanT}
+               "cdprobe_plan_t": a.PlanT, "cdprobe_trace_t": a.TraceT,
+               "cdprobe_topology_t": a.TopologyT}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -119,4 +120,4 @@ def test_product_does_not_reference_the_oracle():
                 assert "cdoracle" not in text and "libcdoracle" not in text, f
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
     out = subprocess.run(["ldd", os.path.join(pkgdir, "libcdprobe.so")], capture_output=True, text=True).stdout
-    assert "cdoracle" not in out and "libcuda" not in out and "nvidia-ml" not in out
+    assert "cdoracle" not in out and "libcuda" not in out and "nvidia-ml" not in out  # NVML/driver are dlopen'ed lazily

@@ -218,3 +218,58 @@ def test_nvml_missing_is_a_clean_error(tmp_path):
 def test_init_failure_is_reported(tmp_path):
     r = poll(tmp_path, "gpus 4\nfail init 9\n")  # NVML_ERROR_DRIVER_NOT_LOADED
     assert r["rc"] == 9
+
+
+# ---- the product's topology enumeration (csrc/topo.cc) must agree with the oracle ----------
+TOPO_CHILD = textwrap.dedent(
+    """
+    import json, sys
+    sys.path.insert(0, %r)
+    import cdprobe_pkg
+    m = cdprobe_pkg.load()
+    try:
+        t = m.topology(strict=bool(int(sys.argv[1])))
+        print(json.dumps({"rc": 0, "n": t.n, "uuids": [t.uuid[i].value.decode() for i in range(t.n)],
+                          "mig": list(t.mig)[:t.n], "links": list(t.links_active)[:t.n],
+                          "clique_id": t.clique_id.decode(), "clique_error": t.clique_error.decode(),
+                          "pci": [t.pci_bus_id[i].value.decode() for i in range(t.n)]}))
+    except m.ProbeError as e:
+        print(json.dumps({"rc": e.code}))
+    """
+) % ROOT
+
+
+def topo(tmp_path, scenario, strict=1, nvml_path=FAKE):
+    sc = tmp_path / "scenario.txt"
+    sc.write_text(scenario)
+    env = dict(os.environ, FAKE_NVML_SCENARIO=str(sc), CDPROBE_NVML_PATH=nvml_path)
+    out = subprocess.run([sys.executable, "-c", TOPO_CHILD, str(strict)], env=env, capture_output=True, text=True,
+                         timeout=60)
+    assert out.returncode == 0, out.stderr
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("scenario", [
+    "gpus 8\n", "gpus 8\nlink_down 3 5\nmig 6 1\n", "gpus 4\nuuid_reverse\n", "gpus 1\n", "gpus 16\n",
+    f"gpus 4\nfabric_all 3 0 7 {UUID}\n", f"gpus 4\nfabric_all 3 0 7 {UUID}\nfabric 2 2 0 7 {UUID}\n",
+    f"gpus 2\nfabric_all 3 0 7 {UUID}\nfabric 1 3 0 8 {UUID}\n", "gpus 4\nunsupported fabric\nunsupported nvlink\n",
+    f"gpus 2\nfabric_all 3 0 7 {UUID}\nfabric 1 3 999 7 {UUID}\n",
+])
+@pytest.mark.parametrize("strict", [1, 0])
+def test_product_topology_agrees_with_oracle(pkg, tmp_path, scenario, strict):
+    """Parity of the host-side mirror of getCliqueID*/device walk: same UUID order, MIG flags, link counts,
+    clique id and error class as the oracle restatement, on every fake-NVML scenario."""
+    t = topo(tmp_path, scenario, strict)
+    o = poll(tmp_path, scenario, flags=0 if strict else 1)
+    assert t["rc"] == 0 and o["rc"] == 0
+    assert t["n"] == o["n"] and t["uuids"] == o["uuids"]
+    assert t["mig"] == o["mig"] and t["links"] == o["n_links"]
+    assert t["clique_id"] == o["clique_id"]
+    assert bool(t["clique_error"]) == bool(o["clique_err"])
+    if t["clique_error"]:
+        assert t["clique_error"] == o["clique_err_text"]
+
+
+def test_product_topology_without_nvml_fails_loudly(pkg, tmp_path):
+    t = topo(tmp_path, "gpus 2\n", nvml_path="/nonexistent/libnvidia-ml.so.1")
+    assert t["rc"] == -3  # CDPROBE_ERR_NO_DEVICE
