@@ -91,7 +91,10 @@ typedef struct {
   uint32_t timeout_ms;                  /* device + host watchdog; 0 = 5000 */
   uint32_t flags;                       /* CDPROBE_FLAG_* */
   uint64_t seed;                        /* 0 = 0xCD5EED0000000001 */
-  float min_fraction;                   /* verdict threshold on pair GB/s / link_peak; 0 = 0.85 */
+  float min_fraction;                   /* verdict threshold on pair GB/s / link_peak; 0 = 0.70.  The north_star's
+                                           0.85 is not a safe gate: a healthy B200 port measures 0.73-0.78 of 900 GB/s
+                                           with both directions loaded and 0.84-0.86 (reads) / 0.77-0.79 (writes) one
+                                           way, so 0.85 would mark healthy nodes NotReady. */
   float link_peak_gbps;                 /* 0 = 900 (NVLink 5, per direction per GPU) */
   uint32_t ctas;                        /* CTAs of the persistent kernel; 0 = one per SM */
   uint32_t world_size;                  /* processes in the probe domain; 0/1 = single process */

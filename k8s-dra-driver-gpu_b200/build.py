@@ -15,6 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcdprobe.so")
+DAEMON = os.path.join(HERE, "cdprobe-daemon")
 SOURCES = ["probe_kernels.cu", "handle.cc", "plan.cc", "rendezvous.cc", "vmm.cc", "topo.cc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -36,7 +37,7 @@ def sources() -> list[str]:
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(DAEMON):
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
@@ -57,6 +58,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         sys.stderr.write(proc.stdout + proc.stderr)
     os.replace(LIB + ".tmp", LIB)
+    # the daemon mirror (host-only C++, no CUDA): cdprobe-daemon {run,check}
+    gxx = shutil.which("g++") or "g++"
+    dcmd = [gxx, "-O2", "-std=c++17", "-Wall", os.path.join(CSRC, "daemon_main.cc"), "-o", DAEMON + ".tmp", "-ldl"]
+    proc = subprocess.run(dcmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(dcmd) + "\n" + proc.stdout + proc.stderr)
+    os.replace(DAEMON + ".tmp", DAEMON)
     return LIB
 
 

@@ -481,7 +481,7 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
   if (c.ops == 0) c.ops = CDPROBE_OP_READ | CDPROBE_OP_WRITE;
   if (c.ops & ~(CDPROBE_OP_READ | CDPROBE_OP_WRITE)) return CDPROBE_ERR_ARG;
   if (c.timeout_ms == 0) c.timeout_ms = 5000;
-  if (c.min_fraction <= 0.f) c.min_fraction = 0.85f;
+  if (c.min_fraction <= 0.f) c.min_fraction = 0.70f;  // see include/cdprobe.h: measured healthy floor on B200
   if (c.link_peak_gbps <= 0.f) c.link_peak_gbps = 900.f;
   if (c.world_size == 0) c.world_size = 1;
   if (c.rank >= c.world_size) return CDPROBE_ERR_ARG;
