@@ -197,7 +197,7 @@ def run_probe(args):
     n = args.gpus
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    grp = pkg.distutil.RankGroup(backend="nccl", device=dev)
+    grp = pkg.distutil.RankGroup(backend="gloo")  # host-side only: barrier + max; the data path uses no collective library
 
     def barrier():
         grp.barrier()
@@ -357,8 +357,10 @@ def run_probe(args):
         if nvl0 and nvl1:
             line["nvlink_counters"] = {
                 "tx_kib_delta": nvl1["tx_kib"] - nvl0["tx_kib"], "rx_kib_delta": nvl1["rx_kib"] - nvl0["rx_kib"],
-                "algorithmic_kib_per_direction": (2 * args.steps + 4) * a_gpu // 1024,
-                "note": "NVML field 138/139 on rank 0's GPU across both timed loops"}
+                "algorithmic_kib_per_direction": (2 * args.steps + 2) * 2 * a_gpu // 1024,
+                "note": "NVML fields 138/139 (NVLink data TX/RX KiB) on rank 0's GPU across both timed loops "
+                        "(2 x steps + 2 probes); per probe each direction carries the write payload and the "
+                        "read responses: 2 x (N-1) x bytes_per_pair"}
         if n == 1 and not args.no_cpu_baseline:
             # fresh process, as the reference's `check` is exec'ed per kubelet probe (NVML init is not
             # amortised): the reference arm of this same script, bounded to ~20 polls

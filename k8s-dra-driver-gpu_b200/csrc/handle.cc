@@ -90,6 +90,7 @@ struct cdprobe {
   uint64_t src_xor[kMaxRanks][kMaxRanks] = {};
   bool sticky = false;
   bool event_timing = false;
+  uint32_t path = 0;          // 0 TMA bulk, 1 ld/st 128-bit, 2 ld/st 256-bit
   uint32_t verify_ctas = 32;  // CTAs that verify landing slots under CDPROBE_FLAG_OVERLAP_VERIFY
   double open_ms = 0, fill_ms = 0;
 };
@@ -327,7 +328,7 @@ static void fill_params(const cdprobe* h, uint32_t li, const Phase* phases, uint
   P->n_ranks = h->n_total;
   P->n_phases = n_phases;
   P->peer_mask = peer_mask;
-  P->use_ldst = (h->cfg.flags & CDPROBE_FLAG_PATH_LDST) ? 1u : 0u;
+  P->use_ldst = h->path;
   P->full_mode = h->plan.full ? 1u : 0u;
   for (uint32_t p = 0; p < n_phases; ++p) {
     P->phase[p] = phases[p];
@@ -485,6 +486,7 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
   if (c.link_peak_gbps <= 0.f) c.link_peak_gbps = 900.f;
   if (c.world_size == 0) c.world_size = 1;
   if (c.rank >= c.world_size) return CDPROBE_ERR_ARG;
+  h->path = (c.flags & CDPROBE_FLAG_PATH_LDST) ? 1u : 0u;
   if (!(c.flags & CDPROBE_FLAG_SERIAL_VERIFY)) c.flags |= CDPROBE_FLAG_OVERLAP_VERIFY;  // overlapped verify is the default
   h->seed = c.seed ? c.seed : kDefaultSeed;
   c.session[sizeof(c.session) - 1] = '\0';
@@ -937,7 +939,7 @@ int cdprobe_info(cdprobe_t* h, cdprobe_info_t* out) {
     }
   }
   out->handle_type = h->handle_type;
-  out->path = (h->cfg.flags & CDPROBE_FLAG_PATH_LDST) ? 1u : 0u;
+  out->path = h->path;
   out->bytes_per_pair = h->plan.bpp;
   out->alloc_bytes = h->plan.alloc_bytes;
   out->n_slices = h->plan.n_slices;
@@ -986,8 +988,8 @@ int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
       }
       return cdp::rebuild_all(h);
     case CDPROBE_OPT_PATH:
-      if (value > 1) return CDPROBE_ERR_ARG;
-      h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_PATH_LDST) | (value ? CDPROBE_FLAG_PATH_LDST : 0u);
+      if (value > 2) return CDPROBE_ERR_ARG;
+      h->path = (uint32_t)value;
       return CDPROBE_OK;
     case CDPROBE_OPT_TIMEOUT_MS:
       if (value == 0 || value > 600000) return CDPROBE_ERR_ARG;

@@ -119,6 +119,24 @@ __device__ __forceinline__ void stg_v4(uint4* p, const uint4& v) {
                "r"(v.w)
                : "memory");
 }
+struct U8 {
+  uint32_t r[8];
+};
+// 256-bit global accesses (sm_100+: LDG.E.256 / STG.E.256) — 1 KiB contiguous per warp instruction.
+__device__ __forceinline__ U8 ldg_v8(const void* p) {
+  U8 v;
+  asm volatile("ld.global.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]),
+                 "=r"(v.r[7])
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg_v8(void* p, const U8& v) {
+  asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v.r[0]),
+               "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3]), "r"(v.r[4]), "r"(v.r[5]), "r"(v.r[6]), "r"(v.r[7])
+               : "memory");
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -262,6 +280,38 @@ __device__ void job_read_ldg(Ctx& c, const uint8_t* base, uint64_t bytes, uint32
   }
 }
 
+__device__ void job_read_ldg256(Ctx& c, const uint8_t* base, uint64_t bytes, uint32_t gwarp, uint32_t nwarps, Sum& a) {
+  const uint64_t n_units = (bytes + kUnitBytes - 1) / kUnitBytes;
+  constexpr int kV = kUnitBytes / 32 / 32;  // 32-byte vectors per lane per full unit
+  for (uint64_t u = gwarp; u < n_units; u += nwarps) {
+    const uint64_t left = bytes - u * kUnitBytes;
+    const uint32_t nvec = (left < kUnitBytes ? static_cast<uint32_t>(left) : kUnitBytes) >> 5;
+    const uint8_t* gp = base + u * kUnitBytes + c.lane * 32u;
+    U8 v[kV];
+    if (nvec == kUnitBytes / 32) {
+#pragma unroll
+      for (int k = 0; k < kV; ++k) v[k] = ldg_v8(gp + k * 1024);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kV; ++k) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[k].r[q] = 0u;
+        if (c.lane + k * 32u < nvec) v[k] = ldg_v8(gp + k * 1024);
+      }
+    }
+    uint64_t ux = 0;
+#pragma unroll
+    for (int k = 0; k < kV; ++k) {
+      const uint64_t w0 = pack64(v[k].r[0], v[k].r[1]), w1 = pack64(v[k].r[2], v[k].r[3]);
+      const uint64_t w2 = pack64(v[k].r[4], v[k].r[5]), w3 = pack64(v[k].r[6], v[k].r[7]);
+      a.s0 += w0 + w2;
+      a.s1 += w1 + w3;
+      ux ^= w0 ^ w1 ^ w2 ^ w3;
+    }
+    fold_unit(a, ux, u);
+  }
+}
+
 // ---------------------------------------------------------- K2: writing ----
 __device__ void job_write_tma(Ctx& c, uint8_t* base, uint64_t bytes, uint32_t gwarp, uint32_t nwarps, uint64_t salt,
                               Sum& a) {
@@ -319,6 +369,36 @@ __device__ void job_write_stg(Ctx& c, uint8_t* base, uint64_t bytes, uint32_t gw
       a.s0 += w0;
       a.s1 += w1;
       ux ^= w0 ^ w1;
+    }
+    fold_unit(a, ux, u);
+  }
+}
+
+__device__ void job_write_stg256(Ctx& c, uint8_t* base, uint64_t bytes, uint32_t gwarp, uint32_t nwarps, uint64_t salt,
+                                 Sum& a) {
+  const uint64_t n_units = (bytes + kUnitBytes - 1) / kUnitBytes;
+  for (uint64_t u = gwarp; u < n_units; u += nwarps) {
+    const uint64_t left = bytes - u * kUnitBytes;
+    const uint32_t nvec = (left < kUnitBytes ? static_cast<uint32_t>(left) : kUnitBytes) >> 5;
+    uint8_t* gp = base + u * kUnitBytes;
+    uint64_t z = (salt + u * (kUnitBytes / 8) + 4ull * c.lane) * kGolden;
+    uint64_t ux = 0;
+#pragma unroll 4
+    for (uint32_t i = c.lane; i < nvec; i += 32) {
+      U8 v;
+      uint64_t zz = z;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint64_t w = zz ^ (zz >> 32);
+        zz += kGolden;
+        v.r[2 * q] = (uint32_t)w;
+        v.r[2 * q + 1] = (uint32_t)(w >> 32);
+        if (q & 1) a.s1 += w;
+        else a.s0 += w;
+        ux ^= w;
+      }
+      z += 128ull * kGolden;
+      stg_v8(gp + (uint64_t)i * 32u, v);
     }
     fold_unit(a, ux, u);
   }
@@ -450,15 +530,18 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
         uint8_t* pb = P.base_peer[job.peer];
         if (job.kind == kJobRead) {
           const uint8_t* src = pb + P.src_off + (P.full_mode ? 0ull : (uint64_t)job.slot * P.bpp);
-          if (P.use_ldst) job_read_ldg(c, src, P.bpp, gwarp, nwarps, a);
+          if (P.use_ldst == 2u) job_read_ldg256(c, src, P.bpp, gwarp, nwarps, a);
+          else if (P.use_ldst == 1u) job_read_ldg(c, src, P.bpp, gwarp, nwarps, a);
           else job_read_tma(c, src, P.bpp, gwarp, nwarps, a);
         } else if (job.kind == kJobVerify) {
           const uint8_t* src = pb + P.land_off + (uint64_t)job.slot * P.bpp;
-          if (P.use_ldst) job_read_ldg(c, src, P.bpp, gwarp, nwarps, a);
+          if (P.use_ldst == 2u) job_read_ldg256(c, src, P.bpp, gwarp, nwarps, a);
+          else if (P.use_ldst == 1u) job_read_ldg(c, src, P.bpp, gwarp, nwarps, a);
           else job_read_tma(c, src, P.bpp, gwarp, nwarps, a);
         } else {
           uint8_t* dst = pb + P.land_off + (uint64_t)job.slot * P.bpp;
-          if (P.use_ldst) job_write_stg(c, dst, P.bpp, gwarp, nwarps, job.salt, a);
+          if (P.use_ldst == 2u) job_write_stg256(c, dst, P.bpp, gwarp, nwarps, job.salt, a);
+          else if (P.use_ldst == 1u) job_write_stg(c, dst, P.bpp, gwarp, nwarps, job.salt, a);
           else job_write_tma(c, dst, P.bpp, gwarp, nwarps, job.salt, a);
         }
       }

@@ -23,6 +23,7 @@ pytestmark = pytest.mark.gpu
 
 NGPU = gpu_count()
 SEED = 0xCD5EED0000000001
+SAME = 0x40 | 0x10  # ALLOW_SAME_DEVICE | NO_COOPERATIVE: several ranks on one device
 
 
 def expected_read(oracle, n, nbytes, mode, i, j, diag=False):
@@ -79,6 +80,27 @@ def test_single_gpu_one_gib(pkg, oracle, path_flag):
         check_full_parity(pkg, oracle, r2, 1, nbytes, pkg.abi.MODE_SLICED, 3)
 
 
+@pytest.mark.parametrize("nbytes", [128, 8192 + 128, 16384 * 3 + 640, (1 << 23) + 128 * 77, 1 << 28])
+def test_path_ldst256_single_gpu(pkg, oracle, nbytes):
+    """Third data path: 256-bit LDG/STG (sm_100 only), selected at run time."""
+    with pkg.Open(pkg.Config(ordinals=[0], bytes=nbytes)) as p:
+        p.SetOption(pkg.abi.OPT_PATH, 2)
+        assert p.Info().path == 2
+        for _ in range(2):
+            r = p.Run()
+            assert r.verdict
+            check_full_parity(pkg, oracle, r, 1, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_path_ldst256_same_device_ranks(pkg, oracle, n):
+    nbytes = (2 << 20) + 128 * 9
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
+        p.SetOption(pkg.abi.OPT_PATH, 2)
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("ops", [1, 2, 3])
 def test_single_gpu_modes_and_ops(pkg, oracle, mode, ops):
@@ -114,7 +136,6 @@ def test_small_grid_and_many_runs(pkg, oracle):
 
 
 # --------------------------------------------- several ranks on one device (one process) ----
-SAME = 0x40 | 0x10  # ALLOW_SAME_DEVICE | NO_COOPERATIVE
 
 
 @pytest.mark.parametrize("path_flag", [0, 0x08], ids=["tma", "ldst"])

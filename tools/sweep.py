@@ -44,7 +44,7 @@ with pkg.Open(pkg.Config(ordinals=list(range(n)), bytes=args.bytes, mode=mode, t
                 rs = [p.Run() for _ in range(args.iters)]
                 off = [(i, j) for i in range(n) for j in range(n) if i != j or n == 1]
                 rec = {
-                    "n": n, "mode": args.mode, "bytes": args.bytes, "path": "ldst" if path else "tma", "ctas": ctas,
+                    "n": n, "mode": args.mode, "bytes": args.bytes, "path": ("tma", "ldst", "ldst256")[path], "ctas": ctas,
                     "overlap": overlap, "uni": uni, "bpp": rs[0].bytes_per_pair, "phases": rs[0].phases,
                     "probe_ms": statistics.median(r.probe_ms for r in rs),
                     "probe_ms_min": min(r.probe_ms for r in rs),
