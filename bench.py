@@ -301,9 +301,18 @@ def run_probe(args):
     a_gpu = (n - 1 if n > 1 else 1) * bpp
     algo_bytes = passes * a_gpu  # per launch (= per GPU per probe)
     achieved = algo_bytes / (value * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f).get(f"n{n}_{args.path}")
+        if t and args.bytes == GIB and args.mode == "sliced":
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        traffic = None
     if n == 1:
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": f"{peak_kind} copy bandwidth",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                    "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this kernel)" if traffic else None, "peak_kind": f"{peak_kind} copy bandwidth",
                     "kernel": "cdprobe_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                     "note": "N=1 loop-back: read 1 GiB + write 1 GiB + verify 1 GiB of local HBM per launch"}
     else:

@@ -126,6 +126,8 @@ typedef struct {
   uint32_t phases;                      /* device phases executed */
   uint32_t launches;                    /* kernels launched by this call (one per local rank) */
   uint32_t aborted;                     /* 1: a device watchdog fired */
+  uint32_t warmed;                      /* 1: this run streamed the link wake-up prefix (phase 0) */
+  uint32_t reserved1;
   double probe_ms;                      /* host wall clock of this cdprobe_run call */
   double device_ms[CDPROBE_MAX_GPUS];   /* per local rank: first barrier release -> last arrive (%globaltimer) */
   double barrier_us[CDPROBE_MAX_GPUS];  /* per local rank: sum of (release - arrive) over all barriers */
@@ -175,7 +177,7 @@ typedef struct {
 typedef struct {
   uint32_t abi;
   uint32_t n_phases;
-  uint8_t kind0[CDPROBE_MAX_PHASES], kind1[CDPROBE_MAX_PHASES];  /* 0 none, 1 read, 2 write, 3 verify */
+  uint8_t kind0[CDPROBE_MAX_PHASES], kind1[CDPROBE_MAX_PHASES];  /* 0 none, 1 read, 2 write, 3 verify, 4 warm-up */
   int8_t peer0[CDPROBE_MAX_PHASES], peer1[CDPROBE_MAX_PHASES];
   uint8_t sync_all[CDPROBE_MAX_PHASES];                          /* closing barrier spans all ranks */
   uint64_t t_start[CDPROBE_MAX_PHASES];                          /* opening barrier released */
@@ -215,6 +217,8 @@ CDPROBE_API int cdprobe_trace(cdprobe_t* h, uint32_t local, cdprobe_trace_t* out
 #define CDPROBE_OPT_OVERLAP_VERIFY 5u /* value 0/1 */
 #define CDPROBE_OPT_VERIFY_CTAS 6u   /* CTAs given to the overlapped verify (default 32) */
 #define CDPROBE_OPT_UNIDIRECTIONAL 7u /* value 0/1: see CDPROBE_FLAG_UNIDIRECTIONAL */
+#define CDPROBE_OPT_WARMUP 8u        /* link wake-up phase: 0 never, 1 auto = after > 1 ms idle (default), 2 always */
+#define CDPROBE_OPT_WARMUP_BYTES 9u  /* bytes each rank streams from its first partner when warming (default 128 MiB, capped at bytes_per_pair) */
 CDPROBE_API int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value);
 /* Storm/unprepare emulation: unmap + remap rank `peer` in local rank `local`'s address space. */
 CDPROBE_API int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer);

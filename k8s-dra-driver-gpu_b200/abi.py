@@ -26,6 +26,7 @@ FLAG_SERIAL_VERIFY = 0x100
 
 OPT_EVENT_TIMING, OPT_CTAS, OPT_PATH, OPT_TIMEOUT_MS, OPT_OVERLAP_VERIFY, OPT_VERIFY_CTAS = 1, 2, 3, 4, 5, 6
 OPT_UNIDIRECTIONAL = 7
+OPT_WARMUP, OPT_WARMUP_BYTES = 8, 9
 
 _N2 = MAX_GPUS * MAX_GPUS
 
@@ -72,6 +73,8 @@ class ResultT(C.Structure):
         ("phases", C.c_uint32),
         ("launches", C.c_uint32),
         ("aborted", C.c_uint32),
+        ("warmed", C.c_uint32),
+        ("reserved1", C.c_uint32),
         ("probe_ms", C.c_double),
         ("device_ms", C.c_double * MAX_GPUS),
         ("barrier_us", C.c_double * MAX_GPUS),

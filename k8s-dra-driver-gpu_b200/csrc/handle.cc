@@ -91,6 +91,11 @@ struct cdprobe {
   bool sticky = false;
   bool event_timing = false;
   uint32_t path = 0;          // 0 TMA bulk, 1 ld/st 128-bit, 2 ld/st 256-bit
+  uint32_t warm_mode = 1;     // 0 never, 1 auto (after an idle gap), 2 always
+  uint64_t warm_bytes = 128ull << 20;
+  double warm_idle_ms = 1.0;  // auto: idle longer than this => links may have left their active state
+  double last_run_end_ms = -1.0;
+  bool warm_now = false;
   uint32_t verify_ctas = 32;  // CTAs that verify landing slots under CDPROBE_FLAG_OVERLAP_VERIFY
   double open_ms = 0, fill_ms = 0;
 };
@@ -237,6 +242,16 @@ static int build_phases(cdprobe* h, uint32_t li) {
   // lower rank of the pair issues first, then the higher — so each ordered pair is measured
   // with its two ports carrying payload one way only (the classic per-link figure).
   const bool uni = (h->cfg.flags & CDPROBE_FLAG_UNIDIRECTIONAL) != 0;
+  if (pl.rounds > 0) {
+    // Phase 0: link wake-up.  After an idle gap the first NVLink transfer of a B200 runs at roughly
+    // half speed for ~200 us (measured: the first read of a cold probe reports 160-375 GB/s), which
+    // would fail healthy pairs.  Every rank streams a prefix of its round-0 partner's slice, untimed;
+    // the phase always exists (all ranks need the same barrier sequence) and each rank decides its
+    // own byte count at launch (0 when the previous run ended less than warm_idle_ms ago).
+    const int p0 = pl.partner[0][g];
+    const bool ok0 = p0 >= 0 && pair_ok(h, g, (uint32_t)p0);
+    push(ok0 ? kJobWarm : kJobNone, ok0 ? p0 : (int)g, ok0 ? slot_of(g, (uint32_t)p0) : 0, 0, true);
+  }
   for (uint32_t r = 0; r < pl.rounds; ++r) {
     const int p = pl.partner[r][g];
     const bool ok = p >= 0 && pair_ok(h, g, (uint32_t)p);
@@ -335,6 +350,7 @@ static void fill_params(const cdprobe* h, uint32_t li, const Phase* phases, uint
     for (int jb = 0; jb < 2; ++jb) {
       Job& job = P->phase[p].job[jb];
       if (job.kind == kJobWrite) job.salt = write_salt(h->seed, L.grank, (uint32_t)job.peer, h->launch_seq);
+      if (job.kind == kJobWarm) job.salt = h->warm_now ? h->warm_bytes : 0ull;
     }
   }
 }
@@ -834,6 +850,8 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
   out->rounds = h->plan.rounds;
   h->launch_seq++;
   out->run_seq = h->launch_seq;
+  h->warm_now = h->warm_mode == 2 ||
+                (h->warm_mode == 1 && (h->last_run_end_ms < 0 || t0 - h->last_run_end_ms > h->warm_idle_ms));
   cdp::ProbeParams P;
   for (uint32_t li = 0; li < h->n_local; ++li) {
     cdp::LocalRank& L = h->lr[li];
@@ -858,7 +876,9 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
     return CDPROBE_ERR_TIMEOUT;
   }
   cdp::assemble(h, out);
-  out->probe_ms = cdp::now_ms() - t0;
+  h->last_run_end_ms = cdp::now_ms();
+  out->probe_ms = h->last_run_end_ms - t0;
+  out->warmed = h->warm_now ? 1u : 0u;
   if (h->event_timing) {  // after probe_ms: the event round trip is not part of the probe
     for (uint32_t li = 0; li < h->n_local; ++li) {
       cdp::LocalRank& L = h->lr[li];
@@ -1017,6 +1037,13 @@ int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
       }
       return rc;
     }
+    case CDPROBE_OPT_WARMUP:
+      if (value > 2) return CDPROBE_ERR_ARG;
+      h->warm_mode = (uint32_t)value;
+      return CDPROBE_OK;
+    case CDPROBE_OPT_WARMUP_BYTES:
+      h->warm_bytes = value / 128 * 128;
+      return CDPROBE_OK;
     case CDPROBE_OPT_VERIFY_CTAS:
       if (value == 0 || value > 65535) return CDPROBE_ERR_ARG;
       h->verify_ctas = (uint32_t)value;

@@ -528,7 +528,16 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
         const uint32_t gwarp = (blockIdx.x - job.cta0) * kWarpsPerCta + c.warp;
         const uint32_t nwarps = (uint32_t)job.nctas * kWarpsPerCta;
         uint8_t* pb = P.base_peer[job.peer];
-        if (job.kind == kJobRead) {
+        if (job.kind == kJobWarm) {
+          // untimed link wake-up: stream a prefix of the partner's slice (result ignored)
+          const uint8_t* src = pb + P.src_off + (P.full_mode ? 0ull : (uint64_t)job.slot * P.bpp);
+          const uint64_t nb = job.salt < P.bpp ? job.salt : P.bpp;
+          if (nb) {
+            if (P.use_ldst == 2u) job_read_ldg256(c, src, nb, gwarp, nwarps, a);
+            else if (P.use_ldst == 1u) job_read_ldg(c, src, nb, gwarp, nwarps, a);
+            else job_read_tma(c, src, nb, gwarp, nwarps, a);
+          }
+        } else if (job.kind == kJobRead) {
           const uint8_t* src = pb + P.src_off + (P.full_mode ? 0ull : (uint64_t)job.slot * P.bpp);
           if (P.use_ldst == 2u) job_read_ldg256(c, src, P.bpp, gwarp, nwarps, a);
           else if (P.use_ldst == 1u) job_read_ldg(c, src, P.bpp, gwarp, nwarps, a);

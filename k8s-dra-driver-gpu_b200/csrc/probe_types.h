@@ -36,7 +36,7 @@ constexpr uint32_t kLdstVecs = 16;         // 16-byte vectors in flight per lane
 constexpr uint64_t kDefaultSeed = 0xCD5EED0000000001ull;
 constexpr uint64_t kGolden = 0x9E3779B97F4A7C15ull;
 
-enum JobKind : uint8_t { kJobNone = 0, kJobRead = 1, kJobWrite = 2, kJobVerify = 3 };
+enum JobKind : uint8_t { kJobNone = 0, kJobRead = 1, kJobWrite = 2, kJobVerify = 3, kJobWarm = 4 };
 enum PhaseCode : int32_t { kCodeOk = 0, kCodeSkipped = 1, kCodeAborted = 2 };
 enum VerdictCode : uint64_t { kVerdictNone = 0, kVerdictOk = 1, kVerdictMismatch = 2, kVerdictNotWritten = 3 };
 
@@ -78,7 +78,7 @@ struct Job {            // 16 bytes
   uint8_t writer;       // verify: rank that wrote the slot
   uint16_t cta0;        // first CTA of the job
   uint16_t nctas;       // CTAs of the job
-  uint64_t salt;        // write pattern salt
+  uint64_t salt;        // write: pattern salt; warm: bytes to stream (0 = skip)
 };
 
 struct Phase {          // 40 bytes

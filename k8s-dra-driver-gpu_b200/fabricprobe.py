@@ -94,6 +94,7 @@ class Result:
     phases: int
     launches: int
     aborted: bool
+    warmed: bool
     probe_ms: float
     device_ms: List[float]
     barrier_us: List[float]
@@ -133,6 +134,7 @@ class Result:
             phases=r.phases,
             launches=r.launches,
             aborted=bool(r.aborted),
+            warmed=bool(r.warmed),
             probe_ms=r.probe_ms,
             device_ms=list(r.device_ms)[:n],
             barrier_us=list(r.barrier_us)[:n],
@@ -192,7 +194,7 @@ class Probe:
         rc = self._lib.cdprobe_trace(self._h, local, C.byref(t))
         if rc != abi.OK:
             _raise(self._lib, rc, "cdprobe_trace")
-        names = {0: "-", 1: "read", 2: "write", 3: "verify"}
+        names = {0: "-", 1: "read", 2: "write", 3: "verify", 4: "warm"}
         return [{"job0": names[t.kind0[p]], "peer0": t.peer0[p], "job1": names[t.kind1[p]], "peer1": t.peer1[p],
                  "sync_all": int(t.sync_all[p]), "t_start": t.t_start[p], "t_end0": t.t_end0[p], "t_end1": t.t_end1[p],
                  "t_arrive": t.t_arrive[p]} for p in range(t.n_phases)]
