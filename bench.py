@@ -21,6 +21,7 @@ metric  = nvlink_probe_ms (lower is better): time to produce the N x N reachabil
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -244,11 +245,13 @@ def run_probe(args):
     # ---- loop B: EXACTLY K steps through the public ABI, barrier + sync on both sides -> e2e
     step()
     host_ms = []
+    warmed = 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
         host_ms.append(out.probe_ms)
+        warmed += int(out.warmed)
     torch.cuda.synchronize()
     t_local = (time.perf_counter() - t0) * 1e3
     barrier()
@@ -261,8 +264,22 @@ def run_probe(args):
     device_ms = max_over_ranks(statistics.mean(dev_ms))
     e2e_ms = max_over_ranks(statistics.mean(host_ms))
 
-    # per-pair GB/s over the whole domain (one extra, gathered run)
-    res = probe.Run(gather=True)
+    # per-pair GB/s over the whole domain: the last timed step's rows, completed across ranks
+    rc = abi.load_library().cdprobe_gather(probe._h, ctypes.byref(out))
+    if rc != abi.OK:
+        raise RuntimeError(f"cdprobe_gather rc={rc}")
+    res = pkg.Result.from_c(out)
+    warmed_steps = max_over_ranks(float(warmed))
+
+    # the daemon's situation: ONE probe after the GPUs sat idle (NVLink leaves its active state);
+    # the library's automatic wake-up phase is part of this number
+    time.sleep(1.0)
+    barrier()
+    cold = probe.Run(gather=True)
+    cold_pairs = [(i, j) for i in range(n) for j in range(n) if i != j or n == 1]
+    cold_start = {"idle_s": 1.0, "probe_ms": max_over_ranks(cold.probe_ms), "warmed": bool(cold.warmed),
+                  "read_min": min(cold.gbps_read[i][j] for i, j in cold_pairs),
+                  "write_min": min(cold.gbps_write[i][j] for i, j in cold_pairs), "verdict": bool(cold.verdict)}
     bpp = res.bytes_per_pair
     pairs_r = [res.gbps_read[i][j] for i in range(n) for j in range(n) if i != j or n == 1]
     pairs_w = [res.gbps_write[i][j] for i in range(n) for j in range(n) if i != j or n == 1]
@@ -359,6 +376,7 @@ def run_probe(args):
                 "worst_step_drop_read": worst_r, "worst_step_drop_write": worst_w, "probe_ms_spread": ev_spread,
             },
             "reachability_all_ones": reach_ok, "verdict": bool(res.verdict),
+            "cold_start": cold_start, "timed_steps_with_wakeup_phase_traffic": warmed_steps,
             "roofline": roofline, "clocks": clocks,
         }
         if uni is not None:

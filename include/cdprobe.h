@@ -217,8 +217,8 @@ CDPROBE_API int cdprobe_trace(cdprobe_t* h, uint32_t local, cdprobe_trace_t* out
 #define CDPROBE_OPT_OVERLAP_VERIFY 5u /* value 0/1 */
 #define CDPROBE_OPT_VERIFY_CTAS 6u   /* CTAs given to the overlapped verify (default 32) */
 #define CDPROBE_OPT_UNIDIRECTIONAL 7u /* value 0/1: see CDPROBE_FLAG_UNIDIRECTIONAL */
-#define CDPROBE_OPT_WARMUP 8u        /* link wake-up phase: 0 never, 1 auto = after > 1 ms idle (default), 2 always */
-#define CDPROBE_OPT_WARMUP_BYTES 9u  /* bytes each rank streams from its first partner when warming (default 128 MiB, capped at bytes_per_pair) */
+#define CDPROBE_OPT_WARMUP 8u        /* link wake-up phase: 0 never, 1 auto = after > 5 ms idle (default), 2 always */
+#define CDPROBE_OPT_WARMUP_BYTES 9u  /* bytes each rank streams from its first partner when warming (default 8 MiB, capped at bytes_per_pair) */
 CDPROBE_API int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value);
 /* Storm/unprepare emulation: unmap + remap rank `peer` in local rank `local`'s address space. */
 CDPROBE_API int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer);

@@ -92,8 +92,8 @@ struct cdprobe {
   bool event_timing = false;
   uint32_t path = 0;          // 0 TMA bulk, 1 ld/st 128-bit, 2 ld/st 256-bit
   uint32_t warm_mode = 1;     // 0 never, 1 auto (after an idle gap), 2 always
-  uint64_t warm_bytes = 128ull << 20;
-  double warm_idle_ms = 1.0;  // auto: idle longer than this => links may have left their active state
+  uint64_t warm_bytes = 8ull << 20;   // measured: the wake-up costs a fixed ~115 us whatever the byte count
+  double warm_idle_ms = 5.0;  // auto: no penalty after 10 ms idle, full penalty after 50 ms (profiles/r01_cold_start_n2.jsonl)
   double last_run_end_ms = -1.0;
   bool warm_now = false;
   uint32_t verify_ctas = 32;  // CTAs that verify landing slots under CDPROBE_FLAG_OVERLAP_VERIFY
@@ -243,11 +243,12 @@ static int build_phases(cdprobe* h, uint32_t li) {
   // with its two ports carrying payload one way only (the classic per-link figure).
   const bool uni = (h->cfg.flags & CDPROBE_FLAG_UNIDIRECTIONAL) != 0;
   if (pl.rounds > 0) {
-    // Phase 0: link wake-up.  After an idle gap the first NVLink transfer of a B200 runs at roughly
-    // half speed for ~200 us (measured: the first read of a cold probe reports 160-375 GB/s), which
-    // would fail healthy pairs.  Every rank streams a prefix of its round-0 partner's slice, untimed;
-    // the phase always exists (all ranks need the same barrier sequence) and each rank decides its
-    // own byte count at launch (0 when the previous run ended less than warm_idle_ms ago).
+    // Phase 0: link wake-up.  After >= ~50 ms of idleness the first NVLink transfer of a B200 pays a
+    // fixed ~115 us before data flows (measured, profiles/r01_cold_start_n2.jsonl; with 38 MB per pair
+    // that made the first read of a cold probe report 160 GB/s and failed healthy pairs).  Every rank
+    // streams a small prefix of its round-0 partner's slice, untimed; the phase always exists (all
+    // ranks need the same barrier sequence) and each rank decides its own byte count at launch (0 when
+    // its previous run ended less than warm_idle_ms ago).
     const int p0 = pl.partner[0][g];
     const bool ok0 = p0 >= 0 && pair_ok(h, g, (uint32_t)p0);
     push(ok0 ? kJobWarm : kJobNone, ok0 ? p0 : (int)g, ok0 ? slot_of(g, (uint32_t)p0) : 0, 0, true);

@@ -187,6 +187,29 @@ def test_runtime_options_round_trip(pkg, oracle):
             p.SetOption(99, 1)
 
 
+def test_wakeup_phase_is_automatic_and_does_not_change_results(pkg, oracle):
+    """Phase 0 (link wake-up) streams bytes only after an idle gap; results are identical either way."""
+    import time
+
+    n, nbytes = 4, 1 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
+        first = p.Run()
+        assert first.warmed  # the first run of a handle is always cold
+        again = p.Run()
+        assert not again.warmed  # back to back: no wake-up traffic
+        time.sleep(0.05)
+        cold = p.Run()
+        assert cold.warmed
+        for r in (first, again, cold):
+            check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+        assert p.Trace(0)[0]["job0"] == "warm"
+        p.SetOption(pkg.abi.OPT_WARMUP, 0)
+        time.sleep(0.05)
+        assert not p.Run().warmed
+        p.SetOption(pkg.abi.OPT_WARMUP, 2)
+        assert p.Run().warmed
+
+
 def test_same_device_with_diagonal(pkg, oracle):
     n, nbytes = 4, 1 << 20
     cfg = pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME | pkg.abi.FLAG_LOCAL_DIAG, ctas=8, timeout_ms=20000)
