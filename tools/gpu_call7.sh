@@ -13,7 +13,7 @@ timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
     bench.py --impl reference --gpus $N --steps 10 --warmup 1 > gpurun_out/ref_n${N}_c7.json 2> gpurun_out/ref_n${N}_c7.err
 echo "ref exit=$?"; cat gpurun_out/ref_n${N}_c7.json | cut -c1-600
 rm -f gpurun_out/sweep_n${N}_c7.jsonl gpurun_out/sweep_full_n${N}_c7.jsonl
-timeout 600 python tools/sweep.py --gpus $N --ctas 148,111 --iters 5 --overlap 1,0 --uni 0,1 --paths 0,1,2 --out gpurun_out/sweep_n${N}_c7.jsonl > gpurun_out/sweep_n${N}_c7.log 2>&1
+timeout 600 python tools/sweep.py --gpus $N --ctas 148,111 --iters 5 --overlap 1 --uni 0,1 --paths 0,2 --out gpurun_out/sweep_n${N}_c7.jsonl > gpurun_out/sweep_n${N}_c7.log 2>&1
 echo "sweep exit=$?"; tail -2 gpurun_out/sweep_n${N}_c7.log | cut -c1-400
 timeout 600 python tools/sweep.py --gpus $N --mode full --ctas 148 --iters 3 --overlap 1 --uni 0 --paths 0 --out gpurun_out/sweep_full_n${N}_c7.jsonl > gpurun_out/sweep_full_n${N}_c7.log 2>&1
 echo "full sweep exit=$?"; cat gpurun_out/sweep_full_n${N}_c7.jsonl | cut -c1-600
