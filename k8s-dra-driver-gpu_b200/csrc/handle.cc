@@ -261,10 +261,8 @@ static int build_phases(cdprobe* h, uint32_t li) {
       const bool i_active = !uni || ((half == 0) == ((int)g < p));
       const bool p_active = !uni || !i_active;
       const bool mine = ok && i_active;
-      if (ops & CDPROBE_OP_READ) {
-        Phase& ph = push(mine ? kJobRead : kJobNone, mine ? p : (int)g, slot, 0, true);
-        if (overlap) attach(ph);
-      }
+      // write first, then read: the slot the partner fills during the write phase is verified by the
+      // spare CTAs during the read phase of the SAME round, so no verify is left over at the end
       if (ops & CDPROBE_OP_WRITE) {
         Phase& ph = push(mine ? kJobWrite : kJobNone, mine ? p : (int)g, slot, 0, true);
         if (overlap) {
@@ -277,6 +275,10 @@ static int build_phases(cdprobe* h, uint32_t li) {
           }
         }
       }
+      if (ops & CDPROBE_OP_READ) {
+        Phase& ph = push(mine ? kJobRead : kJobNone, mine ? p : (int)g, slot, 0, true);
+        if (overlap) attach(ph);
+      }
     }
   }
   if (pl.diag) {
@@ -285,9 +287,12 @@ static int build_phases(cdprobe* h, uint32_t li) {
   }
   if (ops & CDPROBE_OP_WRITE) {
     if (overlap) {
-      // always present (a rank that sat out the last round of an odd-sized domain pushes an idle
-      // phase) so that every rank has the same number of barriers
-      push(pend.have && pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, false);
+      // With reads in the schedule every write phase is followed by a read phase that carried its
+      // verify, on every rank.  Write-only probes keep one trailing verify phase — always present (a
+      // rank that sat out the last round of an odd-sized domain pushes an idle phase) so that every
+      // rank has the same number of barriers.
+      if (!(ops & CDPROBE_OP_READ))
+        push(pend.have && pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, false);
       pend.have = false;
       if (pl.diag) push(kJobVerify, (int)g, pl.diag_slot, g, false);
     } else {

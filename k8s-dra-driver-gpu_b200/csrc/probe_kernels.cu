@@ -438,7 +438,9 @@ __device__ void barrier(const ProbeParams& P, Ctx& c, int b, bool sync_all) {
     const bool ab = aborted(c);
     if (!ab) {
       const unsigned long long target = P.seq_base + (unsigned long long)b + 1ull;
-      __threadfence_system();  // this CTA's (remote) writes are performed before the arrive
+      // This CTA's accumulator atomics precede the arrive.  Remote stores of a write job were already
+      // fenced at system scope by this thread (see the job epilogue), so gpu scope is enough here.
+      __threadfence();
       const unsigned int prev = atomicAdd(&ctrl->grid_arrive, 1u);
       if (prev == gridDim.x - 1) {
         // last arriver: every local CTA is done with the phase
@@ -448,9 +450,12 @@ __device__ void barrier(const ProbeParams& P, Ctx& c, int b, bool sync_all) {
         if (b >= 1) phase_epilogue(P, ctrl, b - 1, false);
         bool timed_out = false;
         if (sync_all) {
+          // One system-scope fence, then relaxed flag stores that pipeline over NVLink.  (A
+          // st.release.sys per peer serialises a round trip per store: ~2 us x 7 peers per barrier.)
+          __threadfence_system();
           for (uint32_t j = 0; j < P.n_ranks; ++j) {
             if (j == P.rank || !((P.peer_mask >> j) & 1u)) continue;
-            st_release_sys(&reinterpret_cast<Ctrl*>(P.base_peer[j])->flags[P.rank].v, target);
+            st_relaxed_sys(&reinterpret_cast<Ctrl*>(P.base_peer[j])->flags[P.rank].v, target);
           }
           for (uint32_t j = 0; j < P.n_ranks && !timed_out; ++j) {
             if (j == P.rank || !((P.peer_mask >> j) & 1u)) continue;
