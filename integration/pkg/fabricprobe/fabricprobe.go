@@ -85,7 +85,7 @@ type Config struct {
 	Ops         uint32
 	TimeoutMs   uint32
 	Flags       uint32
-	MinFraction float32 // FABRIC_PROBE_MIN_FRACTION; 0 = library default (0.70 of 900 GB/s/dir)
+	MinFraction float32 // FABRIC_PROBE_MIN_FRACTION; 0 = library default (0.65 of 900 GB/s/dir)
 }
 
 type Result struct {

@@ -23,10 +23,11 @@ FLAG_OVERLAP_VERIFY = 0x20
 FLAG_ALLOW_SAME_DEVICE = 0x40
 FLAG_UNIDIRECTIONAL = 0x80
 FLAG_SERIAL_VERIFY = 0x100
+FLAG_SIMULATE_MIG = 0x200
 
 OPT_EVENT_TIMING, OPT_CTAS, OPT_PATH, OPT_TIMEOUT_MS, OPT_OVERLAP_VERIFY, OPT_VERIFY_CTAS = 1, 2, 3, 4, 5, 6
 OPT_UNIDIRECTIONAL = 7
-OPT_WARMUP, OPT_WARMUP_BYTES = 8, 9
+OPT_WARMUP, OPT_WARMUP_BYTES, OPT_DEBUG_SKIP_RANK = 8, 9, 10
 
 _N2 = MAX_GPUS * MAX_GPUS
 

@@ -96,6 +96,7 @@ struct cdprobe {
   double warm_idle_ms = 5.0;  // auto: no penalty after 10 ms idle, full penalty after 50 ms (profiles/r01_cold_start_n2.jsonl)
   double last_run_end_ms = -1.0;
   bool warm_now = false;
+  uint32_t debug_skip_rank = 0;  // 1-based local rank whose kernel is NOT launched (fault injection)
   uint32_t verify_ctas = 32;  // CTAs that verify landing slots under CDPROBE_FLAG_OVERLAP_VERIFY
   double open_ms = 0, fill_ms = 0;
 };
@@ -504,7 +505,7 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
   if (c.ops == 0) c.ops = CDPROBE_OP_READ | CDPROBE_OP_WRITE;
   if (c.ops & ~(CDPROBE_OP_READ | CDPROBE_OP_WRITE)) return CDPROBE_ERR_ARG;
   if (c.timeout_ms == 0) c.timeout_ms = 5000;
-  if (c.min_fraction <= 0.f) c.min_fraction = 0.70f;  // see include/cdprobe.h: measured healthy floor on B200
+  if (c.min_fraction <= 0.f) c.min_fraction = 0.65f;  // see include/cdprobe.h: measured healthy floor on B200
   if (c.link_peak_gbps <= 0.f) c.link_peak_gbps = 900.f;
   if (c.world_size == 0) c.world_size = 1;
   if (c.rank >= c.world_size) return CDPROBE_ERR_ARG;
@@ -592,7 +593,7 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
       return CDPROBE_ERR_UNSUPPORTED;
     }
     L.sm_count = prop.multiProcessorCount;
-    L.mig = strstr(prop.name, "MIG") != nullptr;
+    L.mig = strstr(prop.name, "MIG") != nullptr || (c.flags & CDPROBE_FLAG_SIMULATE_MIG);
     format_uuid(prop.uuid, L.mig, L.uuid);
     int coop = 0;
     CDP_RT(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, L.ordinal));
@@ -693,7 +694,8 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
     for (uint32_t j = 0; j < h->n_total; ++j) {
       int32_t st = h->status[L.grank][j];
       if (st == 0) {
-        if (j != L.grank && L.mig && (c.flags & CDPROBE_FLAG_MIG_AWARE)) st = CDPROBE_ERR_UNSUPPORTED;  // no P2P under MIG
+        if (j != L.grank && L.mig && (c.flags & (CDPROBE_FLAG_MIG_AWARE | CDPROBE_FLAG_SIMULATE_MIG)))
+          st = CDPROBE_ERR_UNSUPPORTED;  // no P2P under MIG: identity matrix, "not applicable"
         else st = map_peer(h, li, j);
       }
       h->status[L.grank][j] = st;
@@ -790,6 +792,9 @@ static void assemble(const cdprobe* h, cdprobe_result_t* out) {
     // every off-diagonal cell of this row must have been probed and reachable
     for (uint32_t j = 0; j < h->n_total; ++j) {
       if (j == g) continue;
+      // P2P is not applicable between MIG instances: the cell stays 0 but must not turn a MIG-only
+      // domain NotReady
+      if (h->status[g][j] == CDPROBE_ERR_UNSUPPORTED || h->status[j][g] == CDPROBE_ERR_UNSUPPORTED) continue;
       const uint32_t idx = g * CDPROBE_MAX_GPUS + j;
       if ((h->cfg.ops & CDPROBE_OP_READ) && !out->reach_read[idx]) verdict = false;
       if ((h->cfg.ops & CDPROBE_OP_WRITE) && !out->reach_write[idx]) verdict = false;
@@ -861,6 +866,14 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
   cdp::ProbeParams P;
   for (uint32_t li = 0; li < h->n_local; ++li) {
     cdp::LocalRank& L = h->lr[li];
+    if (h->debug_skip_rank == li + 1) {  // fault injection: this rank never shows up at the barriers
+      memset(L.row->ph, 0, sizeof(L.row->ph));
+      L.row->aborted = 1;
+      L.row->n_phases = L.n_phases;
+      L.row->t_first = L.row->t_last = 0;
+      L.row->done = h->launch_seq;
+      continue;
+    }
     cdp::fill_params(h, li, L.phases, L.n_phases, L.peer_mask, &P);
     if (h->event_timing) {
       cudaSetDevice(L.ordinal);
@@ -903,6 +916,9 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
       }
     }
     cdp::set_err("device watchdog fired (a peer did not reach a barrier within timeout_ms)");
+    // In one process all ranks share the run counter and the handle stays usable.  Across processes
+    // the peers' counters may have diverged: the handle must be reopened.
+    if (h->cfg.world_size > 1) h->sticky = true;
     return CDPROBE_ERR_TIMEOUT;
   }
   return CDPROBE_OK;
@@ -1043,6 +1059,10 @@ int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
       }
       return rc;
     }
+    case CDPROBE_OPT_DEBUG_SKIP_RANK:
+      if (value > h->n_local) return CDPROBE_ERR_ARG;
+      h->debug_skip_rank = (uint32_t)value;
+      return CDPROBE_OK;
     case CDPROBE_OPT_WARMUP:
       if (value > 2) return CDPROBE_ERR_ARG;
       h->warm_mode = (uint32_t)value;

@@ -43,7 +43,7 @@ class Config:
     timeout_ms: int = 5000
     flags: int = 0
     seed: int = 0
-    min_fraction: float = 0.0  # 0 = library default (0.70 of link_peak_gbps)
+    min_fraction: float = 0.0  # 0 = library default (0.65 of link_peak_gbps)
     link_peak_gbps: float = 900.0
     ctas: int = 0
     world_size: int = 1

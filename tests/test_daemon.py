@@ -112,8 +112,8 @@ def test_run_without_gpu_does_not_gate(tmp_path):
 @pytest.mark.gpu
 def test_run_once_writes_a_passing_verdict_and_check_reads_it(tmp_path):
     v = tmp_path / "fabricprobe.json"
-    env = {"COMPUTE_DOMAIN_UUID": "cd-1", "CDPROBE_LIBRARY": LIB, "FABRIC_PROBE_VERDICT_PATH": str(v),
-           "FABRIC_PROBE_BYTES": str(256 << 20)}
+    # defaults on purpose (1 GiB per GPU, library gate): this is what the daemon pod would run
+    env = {"COMPUTE_DOMAIN_UUID": "cd-1", "CDPROBE_LIBRARY": LIB, "FABRIC_PROBE_VERDICT_PATH": str(v)}
     r = daemon(["run", "--once"], env, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "t_fabric_probe" in r.stderr and "fabric probe: verdict ok" in r.stderr

@@ -210,6 +210,46 @@ def test_wakeup_phase_is_automatic_and_does_not_change_results(pkg, oracle):
         assert p.Run().warmed
 
 
+def test_simulated_mig_domain_is_identity_and_not_a_failure(pkg, oracle):
+    """BASELINE config 4 without MIG hardware: no P2P between MIG instances => identity matrix (what the
+    NVML oracle says for an all-MIG node, tests/test_oracle_nvml.py::test_all_mig_is_identity), diagonal
+    measured through local HBM, the run returns, and the verdict is NOT a failure."""
+    n, nbytes = 4, 1 << 20
+    flags = SAME | pkg.abi.FLAG_SIMULATE_MIG | pkg.abi.FLAG_LOCAL_DIAG
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=flags, ctas=8, timeout_ms=20000)) as p:
+        assert all(p.Info().mig[i] == 1 for i in range(n))
+        r = p.Run()
+        ident = [[1 if i == j else 0 for j in range(n)] for i in range(n)]
+        assert r.reach == ident and not r.aborted and r.verdict
+        for i in range(n):
+            assert r.gbps_read[i][i] > 0 and r.gbps_write[i][i] > 0
+            assert (r.sum_read[i][i], r.xor_read[i][i]) == expected_read(oracle, n, nbytes, 1, i, i, diag=True)
+            for j in range(n):
+                if i != j:
+                    assert r.status[i][j] == pkg.abi.ERR_UNSUPPORTED
+
+
+def test_device_watchdog_bounds_a_missing_peer(pkg, oracle):
+    """A rank that never reaches the barrier must not hang the probe (the readiness probe has a 10 s budget,
+    templates/compute-domain-daemon.tmpl.yaml:83): the device watchdog fires after timeout_ms, the call
+    returns CDPROBE_ERR_TIMEOUT with aborted = 1 and nothing reachable, and the handle recovers."""
+    import time
+
+    n, nbytes = 3, 1 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=300)) as p:
+        assert p.Run().reach == [[1] * n for _ in range(n)]
+        p.SetOption(pkg.abi.OPT_DEBUG_SKIP_RANK, 2)  # local rank 1 is never launched
+        t0 = time.time()
+        r = p.Run(allow_timeout=True)
+        assert time.time() - t0 < 5.0
+        assert r.aborted and not r.verdict
+        assert all(r.reach_read[i][j] == 0 for i in range(n) for j in range(n) if i != j)
+        p.SetOption(pkg.abi.OPT_DEBUG_SKIP_RANK, 0)
+        good = p.Run()
+        assert not good.aborted and good.reach == [[1] * n for _ in range(n)]
+        check_full_parity(pkg, oracle, good, n, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
 def test_same_device_with_diagonal(pkg, oracle):
     n, nbytes = 4, 1 << 20
     cfg = pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME | pkg.abi.FLAG_LOCAL_DIAG, ctas=8, timeout_ms=20000)
