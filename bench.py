@@ -361,9 +361,9 @@ def run_probe(args):
                 "handle_type": int(info.handle_type),
             },
             "device_ms_globaltimer": device_ms,
-            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 2776,
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 2768,
                     "d2h_bytes_per_step": 32 + 120 * int(res.phases),
-                    "note": "cdprobe_run from a host thread: kernel parameters (2776 B) in, result row "
+                    "note": "cdprobe_run from a host thread: kernel parameters (2768 B) in, result row "
                             "(pinned host memory written by the kernel) out; the probe's inputs are "
                             "generated on the device by design"},
             "gpu_launches": args.steps * n,

@@ -187,6 +187,20 @@ typedef struct {
   uint64_t t_arrive[CDPROBE_MAX_PHASES];                         /* every local CTA reached the closing barrier */
 } cdprobe_trace_t;
 
+/* The phase table of one rank (host-only; what cdprobe_run hands to that rank's kernel when every pair is mapped). */
+typedef struct {
+  uint32_t abi;
+  uint32_t n_phases;
+  uint32_t peer_mask;                              /* ranks in this rank's cross-GPU barrier */
+  uint32_t reserved;
+  uint8_t kind[2][CDPROBE_MAX_PHASES];             /* [job][phase]: 0 none, 1 read, 2 write, 3 verify, 4 warm-up */
+  int8_t peer[2][CDPROBE_MAX_PHASES];              /* rank whose memory the job touches */
+  uint8_t slot[2][CDPROBE_MAX_PHASES];             /* landing slot (write/verify) or source slice (read/warm) */
+  uint8_t writer[2][CDPROBE_MAX_PHASES];           /* verify: the rank that wrote the slot */
+  uint16_t cta0[2][CDPROBE_MAX_PHASES], nctas[2][CDPROBE_MAX_PHASES];
+  uint8_t sync_all[CDPROBE_MAX_PHASES];            /* closing barrier spans all ranks */
+} cdprobe_schedule_t;
+
 /* Node topology as NVML reports it (no CUDA; internal/common topology enumeration). */
 typedef struct {
   uint32_t abi;
@@ -235,6 +249,8 @@ CDPROBE_API void cdprobe_close(cdprobe_t* h);
 CDPROBE_API int cdprobe_plan(uint32_t n, uint64_t bytes, uint32_t mode, uint32_t flags, cdprobe_plan_t* out);
 /* strict != 0: getCliqueIDStrict (feature gate CrashOnNVLinkFabricErrors, default on), else the legacy walk. */
 CDPROBE_API int cdprobe_topology(uint32_t strict, cdprobe_topology_t* out);
+CDPROBE_API int cdprobe_schedule(uint32_t n, uint32_t rank, uint64_t bytes, uint32_t mode, uint32_t ops, uint32_t flags,
+                                 uint32_t ctas, uint32_t verify_ctas, cdprobe_schedule_t* out);
 CDPROBE_API int cdprobe_rendezvous_selftest(const char* session, uint32_t rank, uint32_t world, uint32_t timeout_ms);
 
 #ifdef __cplusplus

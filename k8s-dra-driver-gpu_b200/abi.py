@@ -154,6 +154,22 @@ class TopologyT(C.Structure):
     ]
 
 
+class ScheduleT(C.Structure):
+    _fields_ = [
+        ("abi", C.c_uint32),
+        ("n_phases", C.c_uint32),
+        ("peer_mask", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("kind", (C.c_uint8 * MAX_PHASES) * 2),
+        ("peer", (C.c_int8 * MAX_PHASES) * 2),
+        ("slot", (C.c_uint8 * MAX_PHASES) * 2),
+        ("writer", (C.c_uint8 * MAX_PHASES) * 2),
+        ("cta0", (C.c_uint16 * MAX_PHASES) * 2),
+        ("nctas", (C.c_uint16 * MAX_PHASES) * 2),
+        ("sync_all", C.c_uint8 * MAX_PHASES),
+    ]
+
+
 # Every symbol include/cdprobe.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "cdprobe_abi_version": (C.c_uint32, []),
@@ -171,6 +187,8 @@ SYMBOLS = {
     "cdprobe_close": (None, [C.c_void_p]),
     "cdprobe_plan": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(PlanT)]),
     "cdprobe_topology": (C.c_int, [C.c_uint32, C.POINTER(TopologyT)]),
+    "cdprobe_schedule": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                   C.c_uint32, C.POINTER(ScheduleT)]),
     "cdprobe_rendezvous_selftest": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32]),
 }
 

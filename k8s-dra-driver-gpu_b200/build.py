@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcdprobe.so")
 DAEMON = os.path.join(HERE, "cdprobe-daemon")
-SOURCES = ["probe_kernels.cu", "handle.cc", "plan.cc", "rendezvous.cc", "vmm.cc", "topo.cc"]
+SOURCES = ["probe_kernels.cu", "handle.cc", "plan.cc", "schedule.cc", "rendezvous.cc", "vmm.cc", "topo.cc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

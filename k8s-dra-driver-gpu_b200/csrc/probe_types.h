@@ -107,7 +107,6 @@ struct ResultRow {      // pinned host memory, written by CTA 0 at the end of a 
 struct ProbeParams {
   uint8_t* base_peer[kMaxRanks];   // rank j's allocation as mapped for this rank; null = unmapped
   ResultRow* row;
-  const uint32_t* host_abort;      // pinned host word; non-zero aborts the kernel
   uint64_t seq_base;               // barrier targets of this run are seq_base + 1 .. + n_phases + 1
   uint64_t run_seq;
   uint64_t timeout_ns;
@@ -119,7 +118,7 @@ struct ProbeParams {
   uint32_t full_mode;              // source has a single slice
   Phase phase[kMaxPhases];
 };
-static_assert(sizeof(ProbeParams) == 2776, "kernel parameter bytes (bench.py reports them as h2d bytes per step)");
+static_assert(sizeof(ProbeParams) == 2768, "kernel parameter bytes (bench.py reports them as h2d bytes per step)");
 static_assert(sizeof(PhaseOut) == 120 && offsetof(ResultRow, ph) == 32, "result row bytes (bench.py: d2h per step)");
 
 // ---- integer definitions shared with the oracle (oracle/pattern.c restates them) ----

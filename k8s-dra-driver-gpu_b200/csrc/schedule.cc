@@ -1,0 +1,188 @@
+// schedule.cc — the phase table one rank's persistent kernel walks (host only, pure function).
+//
+// rounds of the tournament x {write, read}, verification of what peers
+// stored, the link wake-up phase.  Every rank must produce the same NUMBER of phases with the
+// same barrier kinds (the device barrier is indexed by phase), whatever its own role in a phase.
+// Exported through the C ABI as cdprobe_schedule() so the invariants are tested without a GPU
+// (tests/test_schedule.py).
+#include "schedule.h"
+
+#include <string.h>
+
+namespace cdp {
+
+// Phase table of local rank li (SURVEY.md §8d schedule: rounds x {read, write}, then verify).
+// With CDPROBE_FLAG_OVERLAP_VERIFY the landing slot a partner filled in round r is verified by
+// the last `verify_ctas` CTAs while the other CTAs drive round r + 1 over NVLink: local HBM has
+// ~8x the bandwidth of the link, so the verify disappears from the critical path.
+int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint32_t* peer_mask) {
+  const Plan& pl = *in.plan;
+  const uint32_t g = in.rank;
+  const uint32_t ops = in.ops;
+  const uint32_t ctas = in.ctas;
+  auto pair_ok = [&](uint32_t a, uint32_t b) {
+    return in.status == nullptr || (in.status[a][b] == 0 && in.status[b][a] == 0);
+  };
+  uint32_t n = 0;
+  auto set_job = [&](Job& j, uint8_t kind, int peer, uint32_t slot, uint32_t writer, uint32_t cta0, uint32_t nctas) {
+    memset(&j, 0, sizeof(j));
+    j.kind = kind;
+    j.peer = (int8_t)peer;
+    j.slot = (uint8_t)slot;
+    j.writer = (uint8_t)writer;
+    j.cta0 = (uint16_t)cta0;
+    j.nctas = (uint16_t)nctas;
+  };
+  bool overflow = false;
+  Phase scratch;
+  auto push = [&](uint8_t kind, int peer, uint32_t slot, uint32_t writer, bool sync_all) -> Phase& {
+    if (n >= (uint32_t)kMaxPhases) {
+      overflow = true;
+      return scratch;
+    }
+    Phase& p = phases[n++];
+    memset(&p, 0, sizeof(p));
+    set_job(p.job[0], kind, peer, slot, writer, 0, ctas);
+    p.sync_all = sync_all ? 1u : 0u;
+    return p;
+  };
+  const uint32_t vctas = in.verify_ctas;
+  const bool overlap = (in.flags & CDPROBE_FLAG_OVERLAP_VERIFY) && (ops & CDPROBE_OP_WRITE) && pl.rounds > 0 &&
+                       vctas > 0 && ctas >= 2 * vctas;
+  struct Pending {
+    bool have = false, ok = false;
+    uint32_t slot = 0, writer = 0;
+  } pend;
+  auto attach = [&](Phase& p) {  // give the tail CTAs of phase p the pending verify
+    if (!pend.have) return;
+    if (p.job[0].kind != kJobNone) p.job[0].nctas = (uint16_t)(ctas - vctas);
+    set_job(p.job[1], pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, ctas - vctas, vctas);
+    pend.have = false;
+  };
+  // Bidirectional (default): both ranks of a pair issue at once, so every NVLink port carries
+  // data in both directions.  CDPROBE_FLAG_UNIDIRECTIONAL splits a round in two halves — the
+  // lower rank of the pair issues first, then the higher — so each ordered pair is measured
+  // with its two ports carrying payload one way only (the classic per-link figure).
+  const bool uni = (in.flags & CDPROBE_FLAG_UNIDIRECTIONAL) != 0;
+  if (pl.rounds > 0) {
+    // Phase 0: link wake-up.  After >= ~50 ms of idleness the first NVLink transfer of a B200 pays a
+    // fixed ~115 us before data flows (measured, profiles/r01_cold_start_n2.jsonl; with 38 MB per pair
+    // that made the first read of a cold probe report 160 GB/s and failed healthy pairs).  Every rank
+    // streams a small prefix of its round-0 partner's slice, untimed; the phase always exists (all
+    // ranks need the same barrier sequence) and each rank decides its own byte count at launch (0 when
+    // its previous run ended less than warm_idle_ms ago).
+    const int p0 = pl.partner[0][g];
+    const bool ok0 = p0 >= 0 && pair_ok(g, (uint32_t)p0);
+    push(ok0 ? kJobWarm : kJobNone, ok0 ? p0 : (int)g, ok0 ? slot_of(g, (uint32_t)p0) : 0, 0, true);
+  }
+  for (uint32_t r = 0; r < pl.rounds; ++r) {
+    const int p = pl.partner[r][g];
+    const bool ok = p >= 0 && pair_ok(g, (uint32_t)p);
+    const uint32_t slot = ok ? slot_of(g, (uint32_t)p) : 0;
+    for (int half = 0; half < (uni ? 2 : 1); ++half) {
+      const bool i_active = !uni || ((half == 0) == ((int)g < p));
+      const bool p_active = !uni || !i_active;
+      const bool mine = ok && i_active;
+      // write first, then read: the slot the partner fills during the write phase is verified by the
+      // spare CTAs during the read phase of the SAME round, so no verify is left over at the end
+      if (ops & CDPROBE_OP_WRITE) {
+        Phase& ph = push(mine ? kJobWrite : kJobNone, mine ? p : (int)g, slot, 0, true);
+        if (overlap) {
+          attach(ph);
+          if (p >= 0 && p_active) {  // what the partner stores into my landing area during this phase
+            pend.have = true;
+            pend.ok = ok;
+            pend.slot = slot_of((uint32_t)p, g);
+            pend.writer = (uint32_t)p;
+          }
+        }
+      }
+      if (ops & CDPROBE_OP_READ) {
+        Phase& ph = push(mine ? kJobRead : kJobNone, mine ? p : (int)g, slot, 0, true);
+        if (overlap) attach(ph);
+      }
+    }
+  }
+  if (pl.diag) {
+    if (ops & CDPROBE_OP_READ) push(kJobRead, (int)g, pl.diag_slot, 0, false);
+    if (ops & CDPROBE_OP_WRITE) push(kJobWrite, (int)g, pl.diag_slot, 0, false);
+  }
+  if (ops & CDPROBE_OP_WRITE) {
+    if (overlap) {
+      // With reads in the schedule every write phase is followed by a read phase that carried its
+      // verify, on every rank.  Write-only probes keep one trailing verify phase — always present (a
+      // rank that sat out the last round of an odd-sized domain pushes an idle phase) so that every
+      // rank has the same number of barriers.
+      if (!(ops & CDPROBE_OP_READ))
+        push(pend.have && pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, false);
+      pend.have = false;
+      if (pl.diag) push(kJobVerify, (int)g, pl.diag_slot, g, false);
+    } else {
+      for (uint32_t s = 0; s < pl.n_slots; ++s) {
+        uint32_t writer;
+        bool ok;
+        if (pl.diag && s == pl.diag_slot) {
+          writer = g;
+          ok = true;
+        } else {
+          writer = s < g ? s : s + 1;
+          ok = pair_ok(g, writer);
+        }
+        push(ok ? kJobVerify : kJobNone, (int)g, s, writer, false);
+      }
+    }
+  }
+  if (overflow) {
+    *n_phases = 0;
+    return CDPROBE_ERR_ARG;
+  }
+  if (n > 0) phases[n - 1].sync_all = 1u;  // verdicts must be visible before the rows are written
+  *n_phases = n;
+  uint32_t mask = 0;
+  for (uint32_t j = 0; j < pl.n; ++j)
+    if (j != g && pair_ok(g, j)) mask |= 1u << j;
+  *peer_mask = mask;
+  return CDPROBE_OK;
+}
+
+
+}  // namespace cdp
+
+extern "C" int cdprobe_schedule(uint32_t n, uint32_t rank, uint64_t bytes, uint32_t mode, uint32_t ops, uint32_t flags,
+                                uint32_t ctas, uint32_t verify_ctas, cdprobe_schedule_t* out) {
+  if (out == nullptr || rank >= n || ctas == 0 || ctas > 65535u) return CDPROBE_ERR_ARG;
+  cdp::Plan pl;
+  int rc = cdp::make_plan(n, bytes, mode, flags, &pl);
+  if (rc != CDPROBE_OK) return rc;
+  if (ops == 0) ops = CDPROBE_OP_READ | CDPROBE_OP_WRITE;
+  if (!(flags & CDPROBE_FLAG_SERIAL_VERIFY)) flags |= CDPROBE_FLAG_OVERLAP_VERIFY;
+  cdp::ScheduleInput in;
+  in.plan = &pl;
+  in.rank = rank;
+  in.ops = ops;
+  in.flags = flags;
+  in.ctas = ctas;
+  in.verify_ctas = verify_ctas ? verify_ctas : 32u;
+  in.status = nullptr;
+  cdp::Phase ph[cdp::kMaxPhases];
+  uint32_t np = 0, mask = 0;
+  rc = cdp::make_phases(in, ph, &np, &mask);
+  memset(out, 0, sizeof(*out));
+  out->abi = CDPROBE_ABI_VERSION;
+  if (rc != CDPROBE_OK) return rc;
+  out->n_phases = np;
+  out->peer_mask = mask;
+  for (uint32_t p = 0; p < np; ++p) {
+    for (int jb = 0; jb < 2; ++jb) {
+      const cdp::Job& j = ph[p].job[jb];
+      out->kind[jb][p] = j.kind;
+      out->peer[jb][p] = j.peer;
+      out->slot[jb][p] = j.slot;
+      out->writer[jb][p] = j.writer;
+      out->cta0[jb][p] = j.cta0;
+      out->nctas[jb][p] = j.nctas;
+    }
+    out->sync_all[p] = (uint8_t)ph[p].sync_all;
+  }
+  return CDPROBE_OK;
+}

@@ -42,7 +42,7 @@ def test_struct_layout_matches_c(pkg, tmp_path):
     a = pkg.abi
     structs = {"cdprobe_config_t": a.ConfigT, "cdprobe_result_t": a.ResultT, "cdprobe_info_t": a.InfoT,
                "cdprobe_plan_t": a.PlanT, "cdprobe_trace_t": a.TraceT,
-               "cdprobe_topology_t": a.TopologyT}
+               "cdprobe_topology_t": a.TopologyT, "cdprobe_schedule_t": a.ScheduleT}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -1,0 +1,147 @@
+"""Invariants of the phase table every rank's kernel walks (csrc/schedule.cc), checked without a
+GPU through cdprobe_schedule().  These are the properties the device barrier and the parity of the
+matrices rely on:
+
+  * every rank has the same number of phases and the same barrier kinds at every index;
+  * in a phase a rank touches at most one peer over NVLink and is touched by at most one
+    (exclusive endpoints), and the pairing follows the tournament plan;
+  * every ordered pair is read exactly once and written exactly once per run;
+  * every landing slot that is written is verified exactly once, by its owner, strictly later,
+    naming the right writer; overlapped verifies run on CTAs disjoint from the link job;
+  * the table fits CDPROBE_MAX_PHASES or the call refuses.
+"""
+import ctypes as C
+import itertools
+
+import pytest
+
+NONE, READ, WRITE, VERIFY, WARM = 0, 1, 2, 3, 4
+UNI, SERIAL, DIAG = 0x80, 0x100, 0x04
+
+
+def schedule(pkg, n, rank, mode=1, ops=3, flags=0, ctas=148, vctas=32, nbytes=1 << 30):
+    s = pkg.abi.ScheduleT()
+    rc = pkg.abi.load_library().cdprobe_schedule(n, rank, nbytes, mode, ops, flags, ctas, vctas, C.byref(s))
+    return rc, s
+
+
+def table(pkg, n, **kw):
+    out = []
+    for r in range(n):
+        rc, s = schedule(pkg, n, r, **kw)
+        if rc != 0:
+            return rc, None
+        out.append(s)
+    return 0, out
+
+
+def slot_of(i, j):
+    return i if i < j else i - 1
+
+
+CASES = [dict(flags=f, ops=o, ctas=c) for f in (0, UNI, SERIAL, UNI | SERIAL, DIAG, UNI | DIAG)
+         for o in (1, 2, 3) for c in (148, 8)]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 16])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"f{c['flags']:x}-o{c['ops']}-c{c['ctas']}")
+def test_schedule_invariants(pkg, n, case):
+    rc, tabs = table(pkg, n, **case)
+    if rc != 0:
+        # only allowed when the table cannot fit: unidirectional + serial verify at large N
+        assert rc == pkg.abi.ERR_ARG and (case["flags"] & UNI) and n >= 13
+        return
+    flags, ops, ctas = case["flags"], case["ops"], case["ctas"]
+    plan = pkg.plan(n, 1 << 30, 1, flags & DIAG)
+    np_ = tabs[0].n_phases
+    assert np_ <= pkg.abi.MAX_PHASES
+    # same length and barrier kinds on every rank; the last barrier spans all ranks
+    for t in tabs:
+        assert t.n_phases == np_
+        assert list(t.sync_all)[:np_] == list(tabs[0].sync_all)[:np_]
+    if np_:
+        assert tabs[0].sync_all[np_ - 1] == 1
+    reads, writes, verifies = {}, {}, {}
+    for ph in range(np_):
+        touched_by = {}
+        for r, t in enumerate(tabs):
+            k0, k1 = t.kind[0][ph], t.kind[1][ph]
+            assert k1 in (NONE, VERIFY)
+            if k0 in (READ, WRITE, WARM) and t.peer[0][ph] != r:
+                p = t.peer[0][ph]
+                assert 0 <= p < n
+                assert p not in touched_by, "two ranks hit the same peer in one phase"
+                touched_by[p] = r
+                assert t.sync_all[ph] == 1  # remote traffic is always closed by an all-rank barrier
+                # the pairing is the tournament's: p's partner in that round is r
+                assert any(plan.partner[rd][r] == p for rd in range(plan.rounds))
+                if not (flags & UNI) and k0 != WARM:
+                    assert tabs[p].kind[0][ph] == k0 and tabs[p].peer[0][ph] == r  # both ends issue at once
+                if (flags & UNI) and k0 != WARM:
+                    assert tabs[p].kind[0][ph] == NONE  # the partner is passive in this half
+            if k0 == READ:
+                key = (r, t.peer[0][ph])
+                assert key not in reads
+                reads[key] = ph
+                if t.peer[0][ph] != r:
+                    assert t.slot[0][ph] == slot_of(r, t.peer[0][ph])
+            if k0 == WRITE:
+                key = (r, t.peer[0][ph])
+                assert key not in writes
+                writes[key] = ph
+                if t.peer[0][ph] != r:
+                    assert t.slot[0][ph] == slot_of(r, t.peer[0][ph])
+            for jb, k in ((0, k0), (1, k1)):
+                if k == VERIFY:
+                    key = (t.writer[jb][ph], r)  # (writer, owner)
+                    assert t.peer[jb][ph] == r and key not in verifies
+                    verifies[key] = (ph, t.slot[jb][ph])
+            # CTA partitions
+            if k0 != NONE:
+                assert t.cta0[0][ph] == 0 and 0 < t.nctas[0][ph] <= ctas
+            if k1 != NONE:
+                assert t.cta0[1][ph] + t.nctas[1][ph] <= ctas
+                if k0 != NONE:
+                    assert t.cta0[0][ph] + t.nctas[0][ph] <= t.cta0[1][ph]
+    pairs = {(i, j) for i in range(n) for j in range(n) if i != j}
+    diag = {(i, i) for i in range(n)} if (n == 1 or flags & DIAG) else set()
+    if ops & 1:
+        assert set(reads) == pairs | diag
+    else:
+        assert not reads
+    if ops & 2:
+        assert set(writes) == pairs | diag
+        assert set(verifies) == set(writes)  # every written slot is verified exactly once, by its owner
+        for (w, o), (ph, slot) in verifies.items():
+            assert ph > writes[(w, o)] or (w == o and ph > writes[(w, o)])
+            assert slot == (slot_of(w, o) if w != o else n - 1)
+    else:
+        assert not writes and not verifies
+
+
+def test_default_8gpu_table_shape(pkg):
+    """The headline configuration: warm-up, then 7 x (write, read + overlapped verify): 15 phases."""
+    rc, tabs = table(pkg, 8)
+    assert rc == 0 and tabs[0].n_phases == 15
+    t = tabs[3]
+    assert t.kind[0][0] == WARM
+    assert [t.kind[0][p] for p in range(1, 15)] == [WRITE, READ] * 7
+    assert [t.kind[1][p] for p in range(1, 15)] == [NONE, VERIFY] * 7
+    assert all(t.nctas[0][p] == 148 - 32 and t.cta0[1][p] == 116 and t.nctas[1][p] == 32 for p in range(2, 15, 2))
+    assert t.peer_mask == 0xFF & ~(1 << 3)
+
+
+def test_overlap_needs_enough_ctas(pkg):
+    # fewer than 2 x verify_ctas CTAs: falls back to verifying after the rounds
+    rc, tabs = table(pkg, 4, ctas=8, vctas=32)
+    assert rc == 0 and all(tabs[0].kind[1][p] == NONE for p in range(tabs[0].n_phases))
+    assert [tabs[0].kind[0][p] for p in range(tabs[0].n_phases)].count(VERIFY) == 3
+
+
+def test_schedule_rejects_bad_arguments(pkg):
+    lib = pkg.abi.load_library()
+    s = pkg.abi.ScheduleT()
+    assert lib.cdprobe_schedule(8, 8, 1 << 30, 1, 3, 0, 148, 32, C.byref(s)) == pkg.abi.ERR_ARG
+    assert lib.cdprobe_schedule(8, 0, 1 << 30, 1, 3, 0, 0, 32, C.byref(s)) == pkg.abi.ERR_ARG
+    assert lib.cdprobe_schedule(8, 0, 1 << 30, 1, 3, 0, 148, 32, None) == pkg.abi.ERR_ARG
+    assert lib.cdprobe_schedule(17, 0, 1 << 30, 1, 3, 0, 148, 32, C.byref(s)) == pkg.abi.ERR_ARG
