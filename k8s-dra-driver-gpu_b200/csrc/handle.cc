@@ -777,7 +777,7 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
   cdp::assemble(h, out);
   h->last_run_end_ms = cdp::now_ms();
   out->probe_ms = h->last_run_end_ms - t0;
-  out->warmed = h->warm_now ? 1u : 0u;
+  out->warmed = (h->warm_now && h->plan.rounds > 0) ? 1u : 0u;  // N = 1 has no link to wake
   if (h->event_timing) {  // after probe_ms: the event round trip is not part of the probe
     for (uint32_t li = 0; li < h->n_local; ++li) {
       cdp::LocalRank& L = h->lr[li];

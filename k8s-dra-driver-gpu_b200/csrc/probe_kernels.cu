@@ -3,20 +3,22 @@
 // K1 read probe   : every warp streams 8 KiB units of a peer's source slice
 //                   into shared memory with 1-D TMA bulk copies
 //                   (cp.async.bulk.shared::cluster.global + mbarrier complete_tx,
-//                   3 stages in flight per warp) or with 128-bit
-//                   ld.global.nc loads, and folds them into the (S, X) checksum.
+//                   3 stages in flight per warp) or with 128-/256-bit
+//                   ld.global loads, and folds them into the (S, X) checksum.
 // K2 write probe  : every warp generates the write pattern into shared memory
 //                   and pushes it into the peer's landing slot with TMA bulk
-//                   stores (cp.async.bulk.global.shared::cta) or st.global.v4.
+//                   stores (cp.async.bulk.global.shared::cta) or st.global.v4/.v8.
 // K3 barrier      : grid barrier (atomic arrive / release word) whose last
-//                   arriver runs the cross-GPU flag barrier: st.release.sys
-//                   into every peer's Ctrl, ld.acquire.sys on the local copy.
+//                   arriver runs the cross-GPU flag barrier: one fence.sys,
+//                   pipelined st.relaxed.sys epochs into every peer's Ctrl,
+//                   ld.acquire.sys on the local copy.
 // K4 verify/local : the read probe pointed at local HBM (landing slots, source
 //                   slices at open, the N = 1 loop-back).
 //
 // One persistent cooperative kernel per GPU runs every phase of a probe
-// (tournament rounds x {read, write}, verify) so a run costs one launch per
-// GPU; phases are timed with %globaltimer on the issuing GPU.
+// (wake-up, tournament rounds x {write, read + overlapped verify}) so a run
+// costs one launch per GPU; phases are timed with %globaltimer on the issuing
+// GPU.  The phase table comes from schedule.cc.
 //
 // The reference has no kernel for this path; the gate it
 // implements is cmd/compute-domain-daemon/main.go:435-459.
@@ -105,7 +107,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 // 128-bit streaming load (coherent at L2; L1 is not polluted). Not .nc: the
 // verify job reads data a peer wrote earlier in the same kernel.
-__device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
+__device__ __forceinline__ uint4 ldg_stream_v4(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
@@ -260,12 +262,12 @@ __device__ void job_read_ldg(Ctx& c, const uint8_t* base, uint64_t bytes, uint32
     uint4 v[kLdstVecs];
     if (nvec == kUnitBytes / 16) {
 #pragma unroll
-      for (int k = 0; k < (int)kLdstVecs; ++k) v[k] = ldg_nc_v4(gp + k * 32);
+      for (int k = 0; k < (int)kLdstVecs; ++k) v[k] = ldg_stream_v4(gp + k * 32);
     } else {
 #pragma unroll
       for (int k = 0; k < (int)kLdstVecs; ++k) {
         v[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (c.lane + k * 32u < nvec) v[k] = ldg_nc_v4(gp + k * 32);
+        if (c.lane + k * 32u < nvec) v[k] = ldg_stream_v4(gp + k * 32);
       }
     }
     uint64_t ux = 0;
