@@ -375,6 +375,10 @@ def run_probe(args):
                 "run_to_run_spread_read": spread_r, "run_to_run_spread_write": spread_w,
                 "worst_step_drop_read": worst_r, "worst_step_drop_write": worst_w, "probe_ms_spread": ev_spread,
             },
+            "job_throughput_gbps": (n * passes * a_gpu / (value * 1e-3) / 1e9) if n == 1 else
+                                   (n * 2 * a_gpu / (value * 1e-3) / 1e9),
+            "job_throughput_note": "whole-job bytes per probe / probe time: N x (read + write) payload over NVLink "
+                                   "(N = 1: read + write + verify through HBM)",
             "reachability_all_ones": reach_ok, "verdict": bool(res.verdict),
             "cold_start": cold_start, "timed_steps_with_wakeup_phase_traffic": warmed_steps,
             "roofline": roofline, "clocks": clocks,

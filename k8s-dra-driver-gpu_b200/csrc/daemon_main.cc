@@ -206,12 +206,51 @@ bool write_verdict(const std::string& path, const cdprobe_result_t* r, int rc, c
   fprintf(f, " \"min_gbps_read\": %.1f,\n \"min_gbps_write\": %.1f,\n \"probe_ms\": %.3f,\n \"bytes_per_pair\": %llu,\n",
           r ? r->min_gbps_read : 0.f, r ? r->min_gbps_write : 0.f, r ? r->probe_ms : 0.0,
           r ? (unsigned long long)r->bytes_per_pair : 0ull);
+  // the matrices themselves (row-major n x n), for operators: the CRD status stays Ready/NotReady
+  if (r != nullptr) {
+    const char* names[4] = {"reach_read", "reach_write", "gbps_read", "gbps_write"};
+    for (int k = 0; k < 4; ++k) {
+      fprintf(f, " \"%s\": [", names[k]);
+      for (uint32_t i = 0; i < r->n; ++i)
+        for (uint32_t j = 0; j < r->n; ++j) {
+          const uint32_t c = i * CDPROBE_MAX_GPUS + j;
+          if (k == 0) fprintf(f, "%u", (unsigned)r->reach_read[c]);
+          else if (k == 1) fprintf(f, "%u", (unsigned)r->reach_write[c]);
+          else fprintf(f, "%.1f", k == 2 ? r->gbps_read[c] : r->gbps_write[c]);
+          if (!(i == r->n - 1 && j == r->n - 1)) fputc(',', f);
+        }
+      fprintf(f, "],\n");
+    }
+  }
   std::string e = err ? err : "";
   for (char& c : e)
     if (c == '"' || c == '\\' || c == '\n') c = ' ';
   fprintf(f, " \"error\": \"%s\"}\n", e.c_str());
   fclose(f);
-  return rename(tmp.c_str(), path.c_str()) == 0;
+  if (rename(tmp.c_str(), path.c_str()) != 0) return false;
+  // Prometheus textfile: same series the Go daemon would register in pkg/metrics
+  const std::string mpath = env_or("FABRIC_PROBE_METRICS_PATH", "");
+  if (!mpath.empty() && r != nullptr) {
+    const std::string mtmp = mpath + ".tmp";
+    FILE* m = fopen(mtmp.c_str(), "w");
+    if (m != nullptr) {
+      fprintf(m, "# TYPE nvidia_dra_fabric_probe_duration_seconds gauge\nnvidia_dra_fabric_probe_duration_seconds %.6f\n",
+              r->probe_ms / 1e3);
+      fprintf(m, "# TYPE nvidia_dra_fabric_probe_unreachable_pairs gauge\nnvidia_dra_fabric_probe_unreachable_pairs %u\n",
+              unreachable);
+      fprintf(m, "# TYPE nvidia_dra_fabric_probe_pair_gbps gauge\n");
+      for (uint32_t i = 0; i < r->n; ++i)
+        for (uint32_t j = 0; j < r->n; ++j) {
+          if (i == j && r->n > 1) continue;
+          const uint32_t c = i * CDPROBE_MAX_GPUS + j;
+          fprintf(m, "nvidia_dra_fabric_probe_pair_gbps{src=\"%u\",dst=\"%u\",op=\"read\"} %.1f\n", i, j, r->gbps_read[c]);
+          fprintf(m, "nvidia_dra_fabric_probe_pair_gbps{src=\"%u\",dst=\"%u\",op=\"write\"} %.1f\n", i, j, r->gbps_write[c]);
+        }
+      fclose(m);
+      rename(mtmp.c_str(), mpath.c_str());
+    }
+  }
+  return true;
 }
 
 int cmd_run(bool once) {

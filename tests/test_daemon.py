@@ -113,10 +113,17 @@ def test_run_without_gpu_does_not_gate(tmp_path):
 def test_run_once_writes_a_passing_verdict_and_check_reads_it(tmp_path):
     v = tmp_path / "fabricprobe.json"
     # defaults on purpose (1 GiB per GPU, library gate): this is what the daemon pod would run
-    env = {"COMPUTE_DOMAIN_UUID": "cd-1", "CDPROBE_LIBRARY": LIB, "FABRIC_PROBE_VERDICT_PATH": str(v)}
+    m = tmp_path / "fabricprobe.prom"
+    env = {"COMPUTE_DOMAIN_UUID": "cd-1", "CDPROBE_LIBRARY": LIB, "FABRIC_PROBE_VERDICT_PATH": str(v),
+           "FABRIC_PROBE_METRICS_PATH": str(m)}
     r = daemon(["run", "--once"], env, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "t_fabric_probe" in r.stderr and "fabric probe: verdict ok" in r.stderr
     d = json.loads(v.read_text())
     assert d["ok"] is True and d["unreachable_pairs"] == 0 and d["n"] == gpu_count() and d["probe_ms"] > 0
+    n = d["n"]
+    assert len(d["reach_read"]) == n * n and all(x == 1 for x in d["reach_read"]) and len(d["gbps_write"]) == n * n
+    prom = m.read_text()
+    assert "nvidia_dra_fabric_probe_duration_seconds" in prom and "nvidia_dra_fabric_probe_unreachable_pairs 0" in prom
+    assert prom.count("nvidia_dra_fabric_probe_pair_gbps{") == 2 * (n * (n - 1) if n > 1 else 1)
     assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": str(v)}).returncode == 0

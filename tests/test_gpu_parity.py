@@ -377,6 +377,21 @@ def test_multi_gpu_in_process_parity_with_nvml_oracle(pkg, oracle, path_flag):
 
 
 @pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("mode,flags", [(2, 0), (0, 0), (1, 0x80), (2, 0x80 | 0x100), (1, 0x04)],
+                         ids=["full", "reach-only", "sliced-unidirectional", "full-uni-serial", "sliced-diag"])
+def test_multi_gpu_modes_on_real_peers(pkg, oracle, mode, flags):
+    """Every mode / schedule variant across all visible GPUs over real NVLink: same bit-exact bar."""
+    n = min(NGPU, 8)
+    nbytes = 16 << 20
+    with pkg.Open(pkg.Config(ordinals=list(range(n)), bytes=nbytes, mode=mode, flags=flags, timeout_ms=20000)) as p:
+        for _ in range(2):
+            r = p.Run()
+            assert not r.aborted
+            check_full_parity(pkg, oracle, r, n, nbytes, mode, 3, diag=bool(flags & 0x04))
+            assert all(r.reach[i][j] == 1 for i in range(n) for j in range(n))
+
+
+@pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
 def test_config2_two_gpu_64mib_full(pkg, oracle):
     """BASELINE config 2: 2-GPU P2P read/write reachability matrix, 64 MiB buffers, full mode."""
     nbytes = 64 << 20
