@@ -219,6 +219,26 @@ CDPROBE_API const char* cdprobe_strerror(int code);
 /* Detail of the last failure on the calling thread ("cuMemMap: CUDA_ERROR_..."), "" if none. */
 CDPROBE_API const char* cdprobe_last_error(void);
 
+/* Entry points and the reference interface each one extends or stands in for (paths relative to
+ * NVIDIA/k8s-dra-driver-gpu @ 2240711):
+ *
+ *   cdprobe_open      once per daemon process, from run():          cmd/compute-domain-daemon/main.go:212-347
+ *                     (also in the cliqueID == "" branch, main.go:244-250, which today only blocks on ctx)
+ *   cdprobe_run       the probe pass; at start and on every daemon-set change delivered by
+ *                     GetDaemonInfoUpdateChan():                    cmd/compute-domain-daemon/controller.go:137-139,
+ *                     update loops main.go:351-431.  Its verdict is what check() consults next to the IMEX gate:
+ *                                                                   cmd/compute-domain-daemon/main.go:435-459
+ *   cdprobe_close     on ctx cancel, before the child is stopped:   cmd/compute-domain-daemon/main.go:87-102
+ *   cdprobe_topology  NVML device walk + clique id, replaces the ad-hoc walk of getCliqueIDStrict/Legacy:
+ *                                                                   cmd/compute-domain-kubelet-plugin/nvlib.go:195-363,
+ *                     vendor/github.com/NVIDIA/go-nvlib/pkg/nvlib/device/device.go:268-310,464-495
+ *   cdprobe_strerror / cdprobe_last_error   text of the Go error:   fmt.Errorf convention of main.go
+ *   cdprobe_remap_peer / cdprobe_unmap_peer  emulate NodeUnprepare/NodePrepare churn around a live domain:
+ *                                                                   cmd/compute-domain-kubelet-plugin/driver.go:165-232
+ *   cdprobe_gather, cdprobe_info, cdprobe_trace, cdprobe_set_option, cdprobe_corrupt, cdprobe_plan,
+ *   cdprobe_schedule, cdprobe_rendezvous_selftest: diagnostics, benches, fault injection; the reference has
+ *   no counterpart (it has no probe).
+ */
 CDPROBE_API int cdprobe_open(const cdprobe_config_t* cfg, cdprobe_t** out);
 CDPROBE_API int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out);
 /* Collective over all processes of the domain: completes rows of other processes. No-op for world_size <= 1. */
