@@ -12,10 +12,14 @@ from oracle import oracle as o  # noqa: E402
 
 pkg = cdprobe_pkg.load()
 SEED = o.DEFAULT_SEED
-for path in (0, pkg.abi.FLAG_PATH_LDST):
-    for n, mode, nbytes in ((1, 1, (1 << 20) + 128 * 5), (2, 0, 1 << 20), (2, 1, (1 << 19) + 128 * 3), (3, 1, 3 << 18)):
-        flags = path | (0x40 | 0x10 if n > 1 else 0)
+for path in (0, 1, 2):  # TMA bulk, 128-bit ld/st, 256-bit ld/st
+    for n, mode, nbytes, extra in ((1, 1, (1 << 20) + 128 * 5, 0), (2, 0, 1 << 20, 0), (2, 1, (1 << 19) + 128 * 3, 0),
+                                   (3, 1, 3 << 18, 0), (4, 1, 1 << 19, 0x80), (4, 1, 1 << 19, 0x20)):
+        flags = extra | (0x40 | 0x10 if n > 1 else 0)
         with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, mode=mode, flags=flags, ctas=4, timeout_ms=120000)) as p:
+            p.SetOption(pkg.abi.OPT_PATH, path)
+            p.SetOption(pkg.abi.OPT_VERIFY_CTAS, 1)
+            p.SetOption(pkg.abi.OPT_WARMUP, 2)  # exercise the wake-up phase too
             for _ in range(2):
                 r = p.Run()
                 assert not r.aborted
@@ -25,5 +29,5 @@ for path in (0, pkg.abi.FLAG_PATH_LDST):
                             continue
                         assert r.reach_read[i][j] == 1 and r.reach_write[i][j] == 1, (n, mode, i, j)
                         assert (r.sum_read[i][j], r.xor_read[i][j]) == o.expected_read(SEED, n, nbytes, mode, i, j)
-        print("ok", "ldst" if path else "tma", n, mode, nbytes, flush=True)
+        print("ok", ("tma", "ldst", "ldst256")[path], n, mode, nbytes, hex(extra), flush=True)
 print("SANITIZE_TARGET_DONE")
