@@ -130,6 +130,14 @@ def dist_env():
     return rank, world, local
 
 
+def workload_name(n: int, mode: str, nbytes: int) -> str:
+    """The workload both arms answer: validate the N-GPU domain's fabric (N x N reachability matrix)."""
+    if n > 1:
+        return (f"{n}-GPU all-pairs NVLink probe, {mode} mode, {nbytes >> 20} MiB per GPU, "
+                f"read+write+verify (BASELINE configs[2] at {n} GPU)")
+    return f"1-GPU loop-back probe, {nbytes >> 20} MiB buffer, read+write+verify"
+
+
 # --------------------------------------------------------------------- reference arm ----
 def cpu_poll_timing(n_gpus: int, steps: int, warmup: int, budget_s: float):
     """Times the reference's CPU path (oracle/nvml_poll.c: the NVML enumerate + NvLinkState + P2PStatus
@@ -169,7 +177,10 @@ def run_reference(args):
               f"({last.nvml_calls} NVML calls per poll)")
     line.update({
         "value": v, "ms_per_step": v, "steps": len(times), "warmup": args.warmup,
-        "config": {"workload": f"reference CPU path: NVML link/P2P reachability poll, {last.n} GPU(s)",
+        "config": {"workload": workload_name(args.gpus, args.mode, args.bytes),
+                   "reference_path": (f"the reference's CPU answer to the same question: NVML enumerate + NvLinkState + "
+                                      f"P2PStatus poll of {last.n} GPU(s) -> N x N reachability matrix (it moves no bytes "
+                                      f"and measures no bandwidth: SURVEY.md F1)"),
                    "n_gpus_polled": last.n, "threads": 1},
         "cpu_baseline": {"value": v, "unit": "ms", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count(), "median_ms": statistics.median(times),
@@ -351,9 +362,7 @@ def run_probe(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {
-                "workload": (f"{n}-GPU all-pairs NVLink probe, {args.mode} mode, {args.bytes >> 20} MiB per GPU, "
-                             f"read+write+verify (BASELINE configs[2] at {n} GPU)" if n > 1 else
-                             f"1-GPU loop-back probe, {args.bytes >> 20} MiB buffer, read+write+verify"),
+                "workload": workload_name(n, args.mode, args.bytes),
                 "bytes_per_gpu": args.bytes, "bytes_per_pair": bpp, "mode": args.mode, "path": args.path,
                 "ctas": int(info.ctas[0]), "rounds": res.rounds, "phases": res.phases,
                 "parallelism": f"{n} ranks, one process per GPU, no data-path collective",
