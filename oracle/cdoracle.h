@@ -44,6 +44,7 @@ extern "C" {
 #define CDORACLE_FLAG_LEGACY_CLIQUE 0x1u /* getCliqueIDLegacy instead of Strict (gate CrashOnNVLinkFabricErrors off) */
 #define CDORACLE_FLAG_NO_ENUMERATE 0x2u  /* skip the config-1 enumerate leg */
 #define CDORACLE_FLAG_NO_IMEX_CTL 0x4u   /* do not exec nvidia-imex-ctl even when CLIQUE_ID is set */
+#define CDORACLE_FLAG_THREADS 0x8u       /* one worker thread per GPU for the link and P2P polls */
 
 typedef struct {
   uint32_t n;                                    /* GPUs NVML enumerates (after n_max clamp) */

@@ -24,6 +24,7 @@
 #define _GNU_SOURCE
 #include <dlfcn.h>
 #include <nvml.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -135,6 +136,79 @@ static int imex_ctl_ready(void) {
   waitpid(pid, &st, 0);
   if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) return 0;
   return strcmp(buf, "READY\n") == 0;
+}
+
+/* ---- optional N-thread variant of the two polls ("single thread and an N-thread variant").
+ * One worker per GPU; NVML is thread-safe but serialises most calls on the RM lock, so this is what "all the
+ * host threads it can use" buys the reference path. ---- */
+typedef struct {
+  nvml_t* nv;
+  nvmlDevice_t* dev;
+  unsigned int count, i;
+  cdoracle_nvml_t* out;
+  uint32_t calls;
+  int phase; /* 0 link poll, 1 P2P poll */
+} worker_t;
+
+static void poll_links_of(nvml_t* nv, nvmlDevice_t* dev, unsigned int i, cdoracle_nvml_t* out, uint32_t* calls) {
+  unsigned int cur = 0, pend = 0;
+  nvmlReturn_t ret = nv->DeviceGetMigMode(dev[i], &cur, &pend);
+  (*calls)++;
+  out->mig_enabled[i] = (ret == NVML_SUCCESS && cur == NVML_DEVICE_MIG_ENABLE) ? 1 : 0;
+  out->n_links[i] = 0;
+  for (unsigned int l = 0; l < CDORACLE_MAX_LINKS; ++l) {
+    nvmlEnableState_t st = NVML_FEATURE_DISABLED;
+    ret = nv->DeviceGetNvLinkState(dev[i], l, &st);
+    (*calls)++;
+    /* NOT_SUPPORTED / INVALID_ARGUMENT for absent links => inactive */
+    const int active = (ret == NVML_SUCCESS && st == NVML_FEATURE_ENABLED);
+    out->link_active[i][l] = (uint8_t)active;
+    out->n_links[i] += (uint8_t)active;
+  }
+}
+
+static void poll_p2p_of(nvml_t* nv, nvmlDevice_t* dev, unsigned int count, unsigned int i, cdoracle_nvml_t* out,
+                        uint32_t* calls) {
+  for (unsigned int j = 0; j < count; ++j) {
+    if (i == j) continue;
+    const nvmlGpuP2PCapsIndex_t idx[3] = {NVML_P2P_CAPS_INDEX_NVLINK, NVML_P2P_CAPS_INDEX_READ, NVML_P2P_CAPS_INDEX_WRITE};
+    int32_t* dst[3] = {out->p2p_nvlink, out->p2p_read, out->p2p_write};
+    for (int k = 0; k < 3; ++k) {
+      nvmlGpuP2PStatus_t st = NVML_P2P_STATUS_UNKNOWN;
+      nvmlReturn_t ret = nv->DeviceGetP2PStatus(dev[i], dev[j], idx[k], &st);
+      (*calls)++;
+      dst[k][i * CDORACLE_MAX_GPUS + j] = ret == NVML_SUCCESS ? (int32_t)st : -(int32_t)ret;
+    }
+  }
+}
+
+static void* worker_main(void* arg) {
+  worker_t* w = (worker_t*)arg;
+  if (w->phase == 0) poll_links_of(w->nv, w->dev, w->i, w->out, &w->calls);
+  else poll_p2p_of(w->nv, w->dev, w->count, w->i, w->out, &w->calls);
+  return NULL;
+}
+
+static uint32_t run_phase(nvml_t* nv, nvmlDevice_t* dev, unsigned int count, cdoracle_nvml_t* out, int phase, int threaded) {
+  uint32_t calls = 0;
+  if (!threaded || count < 2) {
+    for (unsigned int i = 0; i < count; ++i) {
+      if (phase == 0) poll_links_of(nv, dev, i, out, &calls);
+      else poll_p2p_of(nv, dev, count, i, out, &calls);
+    }
+    return calls;
+  }
+  pthread_t th[CDORACLE_MAX_GPUS];
+  worker_t w[CDORACLE_MAX_GPUS];
+  for (unsigned int i = 0; i < count; ++i) {
+    w[i] = (worker_t){nv, dev, count, i, out, 0, phase};
+    pthread_create(&th[i], NULL, worker_main, &w[i]);
+  }
+  for (unsigned int i = 0; i < count; ++i) {
+    pthread_join(th[i], NULL);
+    calls += w[i].calls;
+  }
+  return calls;
 }
 
 int cdoracle_nvml_poll(uint32_t n_max, uint32_t flags, cdoracle_nvml_t* out) {
@@ -332,39 +406,12 @@ int cdoracle_nvml_poll(uint32_t n_max, uint32_t flags, cdoracle_nvml_t* out) {
 
   /* ---- MIG mode + NvLink state poll: N x 18 calls -------------------------------- */
   t0 = now_ms();
-  for (unsigned int i = 0; i < count; ++i) {
-    unsigned int cur = 0, pend = 0;
-    ret = nv.DeviceGetMigMode(dev[i], &cur, &pend);
-    calls++;
-    out->mig_enabled[i] = (ret == NVML_SUCCESS && cur == NVML_DEVICE_MIG_ENABLE) ? 1 : 0;
-    for (unsigned int l = 0; l < CDORACLE_MAX_LINKS; ++l) {
-      nvmlEnableState_t st = NVML_FEATURE_DISABLED;
-      ret = nv.DeviceGetNvLinkState(dev[i], l, &st);
-      calls++;
-      /* NOT_SUPPORTED / INVALID_ARGUMENT for absent links => inactive */
-      const int active = (ret == NVML_SUCCESS && st == NVML_FEATURE_ENABLED);
-      out->link_active[i][l] = (uint8_t)active;
-      out->n_links[i] += (uint8_t)active;
-    }
-  }
+  calls += run_phase(&nv, dev, count, out, 0, (flags & CDORACLE_FLAG_THREADS) != 0);
   out->link_poll_ms = now_ms() - t0;
 
   /* ---- P2P status poll: N(N-1) x {NVLINK, READ, WRITE} ----------------------------- */
   t0 = now_ms();
-  for (unsigned int i = 0; i < count; ++i) {
-    for (unsigned int j = 0; j < count; ++j) {
-      if (i == j) continue;
-      const nvmlGpuP2PCapsIndex_t idx[3] = {NVML_P2P_CAPS_INDEX_NVLINK, NVML_P2P_CAPS_INDEX_READ,
-                                            NVML_P2P_CAPS_INDEX_WRITE};
-      int32_t* dst[3] = {out->p2p_nvlink, out->p2p_read, out->p2p_write};
-      for (int k = 0; k < 3; ++k) {
-        nvmlGpuP2PStatus_t st = NVML_P2P_STATUS_UNKNOWN;
-        ret = nv.DeviceGetP2PStatus(dev[i], dev[j], idx[k], &st);
-        calls++;
-        dst[k][i * CDORACLE_MAX_GPUS + j] = ret == NVML_SUCCESS ? (int32_t)st : -(int32_t)ret;
-      }
-    }
-  }
+  calls += run_phase(&nv, dev, count, out, 1, (flags & CDORACLE_FLAG_THREADS) != 0);
   out->p2p_poll_ms = now_ms() - t0;
 
   /* ---- IMEX gate (only when the node has a clique: main.go:436-439) ---------------- */

@@ -20,6 +20,7 @@ _N2 = MAX_GPUS * MAX_GPUS
 FLAG_LEGACY_CLIQUE = 0x1
 FLAG_NO_ENUMERATE = 0x2
 FLAG_NO_IMEX_CTL = 0x4
+FLAG_THREADS = 0x8
 
 
 class NvmlT(C.Structure):

@@ -75,6 +75,6 @@ def test_reference_arm_only_rank0_prints(oracle, tmp_path):
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"] == "nvlink_probe_ms" and j["unit"] == "ms"
     assert j["higher_is_better"] is False and j["n_gpus"] == 2 and j["value"] > 0
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] == 1
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] in (1, 2)
     assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
     assert j["reach_all_ones"] is True

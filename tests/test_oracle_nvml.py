@@ -210,6 +210,16 @@ def test_imex_gate_noop_without_clique(tmp_path):
     assert r["imex_gate"] == -1 and r["reach"] == ones(4)
 
 
+@pytest.mark.parametrize("scenario", ["gpus 8\n", "gpus 8\nlink_down 3 5\nmig 6 1\np2p 2 5 nvlink 6\n", "gpus 1\n",
+                                      "gpus 16\np2p 0 15 read 3\n"])
+def test_threaded_poll_gives_the_same_answer(tmp_path, scenario):
+    """The N-thread variant of the link/P2P polls (one worker per GPU) is only a timing variant."""
+    a = poll(tmp_path, scenario, flags=0)
+    b = poll(tmp_path, scenario, flags=8)
+    for k in ("rc", "n", "reach", "n_links", "mig", "clique_id", "calls", "uuids"):
+        assert a[k] == b[k], k
+
+
 def test_nvml_missing_is_a_clean_error(tmp_path):
     r = poll(tmp_path, "gpus 4\n", nvml_path="/nonexistent/libnvidia-ml.so.1")
     assert r["rc"] == -1
