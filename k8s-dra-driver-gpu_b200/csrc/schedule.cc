@@ -103,9 +103,21 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
       }
     }
   }
+  // Loop-back (N = 1, or CDPROBE_FLAG_LOCAL_DIAG): same shape as a round — write the diagonal slot,
+  // then read the source slice on half the CTAs while the other half verifies what was just written
+  // (both jobs are HBM-bound, hence the even split).  One barrier fewer than read / write / verify.
+  const bool diag_overlap = pl.diag && (in.flags & CDPROBE_FLAG_OVERLAP_VERIFY) && (ops & CDPROBE_OP_WRITE) &&
+                            (ops & CDPROBE_OP_READ) && ctas >= 2;
   if (pl.diag) {
-    if (ops & CDPROBE_OP_READ) push(kJobRead, (int)g, pl.diag_slot, 0, false);
     if (ops & CDPROBE_OP_WRITE) push(kJobWrite, (int)g, pl.diag_slot, 0, false);
+    if (ops & CDPROBE_OP_READ) {
+      Phase& ph = push(kJobRead, (int)g, pl.diag_slot, 0, false);
+      if (diag_overlap) {
+        const uint32_t half = ctas / 2;
+        ph.job[0].nctas = (uint16_t)(ctas - half);
+        set_job(ph.job[1], kJobVerify, (int)g, pl.diag_slot, g, ctas - half, half);
+      }
+    }
   }
   if (ops & CDPROBE_OP_WRITE) {
     if (overlap) {
@@ -116,12 +128,13 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
       if (!(ops & CDPROBE_OP_READ))
         push(pend.have && pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, false);
       pend.have = false;
-      if (pl.diag) push(kJobVerify, (int)g, pl.diag_slot, g, false);
+      if (pl.diag && !diag_overlap) push(kJobVerify, (int)g, pl.diag_slot, g, false);
     } else {
       for (uint32_t s = 0; s < pl.n_slots; ++s) {
         uint32_t writer;
         bool ok;
         if (pl.diag && s == pl.diag_slot) {
+          if (diag_overlap) continue;  // already verified next to the loop-back read
           writer = g;
           ok = true;
         } else {
