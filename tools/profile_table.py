@@ -26,7 +26,7 @@ for n in (1, 2, 4, 8):
     probe = f"{b['value']:.3f}"
     if n == 1:
         probe += f" (3 GiB HBM: {rf['achieved']:.0f} GB/s = {rf['frac']:.3f} of measured {rf['peak']:.0f})"
-        pair = f"loop-back {pl['read_min']:.0f} · {pl['write_min']:.0f}"
+        pair = f"loop-back: write {pl['write_min']:.0f}, then read {pl['read_min']:.0f} concurrent with the verify"
     else:
         pair = f"{pl['read_min']:.0f}–{pl['read_max']:.0f} · {pl['write_min']:.0f}–{pl['write_max']:.0f}"
     uni = "—" if not u else f"{u['read_min']:.0f}–{u['read_median']:.0f} (min–median) · {u['write_min']:.0f}–{u['write_median']:.0f} ({u['probe_ms']:.2f})"
