@@ -215,6 +215,9 @@ def run_probe(args):
     if world == 1 and args.gpus > 1:
         raise SystemExit("launch N > 1 with torchrun: one process per GPU")
     n = args.gpus
+    # one visible GPU per rank (a launcher that sets CUDA_VISIBLE_DEVICES per process): the ordinal is 0
+    if torch.cuda.device_count() <= local:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     grp = pkg.distutil.RankGroup(backend="gloo")  # host-side only: barrier + max; the data path uses no collective library
