@@ -391,6 +391,20 @@ def test_multi_gpu_modes_on_real_peers(pkg, oracle, mode, flags):
             assert all(r.reach[i][j] == 1 for i in range(n) for j in range(n))
 
 
+@pytest.mark.skipif(NGPU < 3, reason="needs >= 3 GPUs")
+@pytest.mark.parametrize("ordinals", [[0, 1, 2], [2, 0, 1], [1, 2]], ids=["0-1-2", "2-0-1", "1-2"])
+def test_odd_sized_and_permuted_domains_on_real_peers(pkg, oracle, ordinals):
+    """An odd-sized domain (one rank sits out every round) and rank != ordinal, over real NVLink."""
+    n, nbytes = len(ordinals), 24 << 20
+    with pkg.Open(pkg.Config(ordinals=ordinals, bytes=nbytes, timeout_ms=20000)) as p:
+        info = p.Info()
+        assert [info.ordinal[i] for i in range(n)] == ordinals
+        r = p.Run()
+        assert not r.aborted and r.rounds == (n if n % 2 else n - 1)
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+        assert r.reach == [[1] * n for _ in range(n)]
+
+
 @pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
 def test_config2_two_gpu_64mib_full(pkg, oracle):
     """BASELINE config 2: 2-GPU P2P read/write reachability matrix, 64 MiB buffers, full mode."""
