@@ -242,14 +242,13 @@ static void fill_params(const cdprobe* h, uint32_t li, const Phase* phases, uint
   }
 }
 
-// Waits until every listed row carries `token`; returns false on host timeout.
-static bool wait_rows(cdprobe* h, uint64_t token, const bool* active) {
+// Waits until every local row carries `token`; returns false on host timeout or a kernel error.
+static bool wait_rows(cdprobe* h, uint64_t token) {
   const double t_end = now_ms() + h->cfg.timeout_ms + 2000.0;
   uint32_t spins = 0;
   for (;;) {
     bool all = true;
     for (uint32_t li = 0; li < h->n_local; ++li) {
-      if (active && !active[li]) continue;
       if (h->lr[li].row->done != token) {
         all = false;
         break;
@@ -323,7 +322,7 @@ static int fill_and_publish(cdprobe* h) {
     const int rc = launch_one(h, li, P);
     if (rc != CDPROBE_OK) return rc;
   }
-  if (!wait_rows(h, h->launch_seq, nullptr)) {
+  if (!wait_rows(h, h->launch_seq)) {
     h->sticky = true;
     if (g_last_error.empty()) set_err("timeout computing source checksums");
     return CDPROBE_ERR_TIMEOUT;
@@ -631,7 +630,7 @@ static void assemble(const cdprobe* h, cdprobe_result_t* out) {
     }
     if (row->aborted) out->aborted = 1;
     out->device_ms[li] = row->t_last > row->t_first ? (double)(row->t_last - row->t_first) / 1e6 : 0.0;
-    double bar_ns = row->n_phases ? 0.0 : 0.0;
+    double bar_ns = 0.0;
     for (uint32_t p = 0; p < L.n_phases; ++p) {
       const PhaseOut& o = row->ph[p];
       if (p + 1 < L.n_phases) {
@@ -768,7 +767,7 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
     out->launches++;
     out->phases = L.n_phases;
   }
-  if (!cdp::wait_rows(h, h->launch_seq, nullptr)) {
+  if (!cdp::wait_rows(h, h->launch_seq)) {
     h->sticky = true;
     if (cdp::g_last_error.empty()) cdp::set_err("host watchdog: kernels did not report within timeout_ms + 2 s");
     out->probe_ms = cdp::now_ms() - t0;
