@@ -456,6 +456,10 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
 
   const bool want_fabric = (c.flags & CDPROBE_FLAG_FABRIC_HANDLES) && imex_channel0_present();
   h->handle_type = want_fabric ? 8u : (c.world_size > 1 ? 1u : 0u);
+  if (c.world_size > 1 && h->rdv.is_tcp() && !want_fabric) {
+    set_err("a tcp: rendezvous spans nodes: it needs CDPROBE_FLAG_FABRIC_HANDLES and /dev/nvidia-caps-imex-channels/channel0");
+    return CDPROBE_ERR_UNSUPPORTED;
+  }
 
   // ---- per local rank: device, stream, allocation, result row -------------
   for (uint32_t li = 0; li < h->n_local; ++li) {

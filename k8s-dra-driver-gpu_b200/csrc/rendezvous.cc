@@ -1,8 +1,12 @@
 // rendezvous.cc — see rendezvous.h.
 #include "rendezvous.h"
 
+#include <arpa/inet.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
 #include <poll.h>
 #include <string.h>
 #include <sys/mman.h>
@@ -35,7 +39,20 @@ socklen_t make_addr(const std::string& session, sockaddr_un* a) {
   return (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + name.size());
 }
 
+// "tcp:<host>:<port>" — the cross-node transport: rank 0 listens on <port>, the others
+// connect to <host>.  Only blobs can travel (fabric handles are 64-byte blobs); fds cannot leave a node.
+bool parse_tcp(const std::string& session, std::string* host, std::string* port) {
+  if (session.compare(0, 4, "tcp:") != 0) return false;
+  const size_t c = session.rfind(':');
+  if (c == std::string::npos || c <= 4) return false;
+  *host = session.substr(4, c - 4);
+  *port = session.substr(c + 1);
+  return !host->empty() && !port->empty();
+}
+
 void set_timeouts(int fd, uint32_t ms) {
+  int one = 1;
+  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));  // no-op (ENOTSUP) on unix sockets
   timeval tv;
   tv.tv_sec = ms / 1000;
   tv.tv_usec = (ms % 1000) * 1000;
@@ -145,12 +162,41 @@ int Rendezvous::connect(const std::string& session, uint32_t rank, uint32_t worl
     if (err) *err = "rendezvous: bad rank/world/session";
     return -EINVAL;
   }
-  sockaddr_un addr;
-  const socklen_t alen = make_addr(session, &addr);
+  sockaddr_storage addr;
+  socklen_t alen = 0;
+  int family = AF_UNIX;
+  memset(&addr, 0, sizeof(addr));
+  std::string host, port;
+  tcp_ = parse_tcp(session, &host, &port);
+  if (session.compare(0, 4, "tcp:") == 0 && !tcp_) {
+    if (err) *err = "rendezvous: expected tcp:<host>:<port>";
+    return -EINVAL;
+  }
+  if (tcp_) {
+    addrinfo hints, *res = nullptr;
+    memset(&hints, 0, sizeof(hints));
+    hints.ai_family = AF_INET;
+    hints.ai_socktype = SOCK_STREAM;
+    if (rank == 0) hints.ai_flags = AI_PASSIVE;
+    if (getaddrinfo(rank == 0 ? nullptr : host.c_str(), port.c_str(), &hints, &res) != 0 || res == nullptr) {
+      if (err) *err = "rendezvous: cannot resolve " + host + ":" + port;
+      return -EHOSTUNREACH;
+    }
+    memcpy(&addr, res->ai_addr, res->ai_addrlen);
+    alen = (socklen_t)res->ai_addrlen;
+    family = AF_INET;
+    freeaddrinfo(res);
+  } else {
+    alen = make_addr(session, reinterpret_cast<sockaddr_un*>(&addr));
+  }
   const double t_end = now_ms() + timeout_ms_;
   if (rank == 0) {
-    listen_fd_ = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+    listen_fd_ = ::socket(family, SOCK_STREAM | SOCK_CLOEXEC, 0);
     if (listen_fd_ < 0) return -errno;
+    if (tcp_) {
+      int one = 1;
+      setsockopt(listen_fd_, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    }
     if (::bind(listen_fd_, reinterpret_cast<sockaddr*>(&addr), alen) < 0 || ::listen(listen_fd_, (int)world) < 0) {
       const int e = errno;
       if (err) *err = std::string("rendezvous: bind/listen: ") + strerror(e);
@@ -178,7 +224,7 @@ int Rendezvous::connect(const std::string& session, uint32_t rank, uint32_t worl
     }
   } else {
     for (;;) {
-      hub_fd_ = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+      hub_fd_ = ::socket(family, SOCK_STREAM | SOCK_CLOEXEC, 0);
       if (hub_fd_ < 0) return -errno;
       if (::connect(hub_fd_, reinterpret_cast<sockaddr*>(&addr), alen) == 0) break;
       const int e = errno;
@@ -226,6 +272,10 @@ int Rendezvous::barrier(std::string* err) {
 int Rendezvous::allgather_fds(const int* mine, uint32_t k, std::vector<int>* all, std::string* err) {
   all->assign((size_t)world_ * k, -1);
   int rc = 0;
+  if (tcp_ && world_ > 1) {
+    if (err) *err = "rendezvous: file descriptors cannot cross nodes (tcp: transport needs fabric handles)";
+    return -ENOTSUP;
+  }
   if (world_ <= 1) {
     for (uint32_t i = 0; i < k; ++i) (*all)[i] = fcntl(mine[i], F_DUPFD_CLOEXEC, 0);
     return 0;
@@ -258,6 +308,20 @@ extern "C" int cdprobe_rendezvous_selftest(const char* session, uint32_t rank, u
   cdp::Rendezvous rdv;
   std::string err;
   if (rdv.connect(session, rank, world, timeout_ms, &err) != 0) return CDPROBE_ERR_RENDEZVOUS;
+  if (rdv.is_tcp()) {
+    // cross-node transport: blobs only (what carries CUmemFabricHandle), plus the barrier
+    uint64_t blob[8], got[8 * CDPROBE_MAX_GPUS * 4];
+    if (world > CDPROBE_MAX_GPUS * 4) return CDPROBE_ERR_ARG;
+    for (int i = 0; i < 8; ++i) blob[i] = 0xFAB51C0000000000ull + ((uint64_t)rank << 8) + (uint64_t)i;
+    if (rdv.allgather(blob, sizeof(blob), got, &err) != 0) return CDPROBE_ERR_RENDEZVOUS;
+    for (uint32_t r = 0; r < world; ++r)
+      for (int i = 0; i < 8; ++i)
+        if (got[r * 8 + i] != 0xFAB51C0000000000ull + ((uint64_t)r << 8) + (uint64_t)i) return CDPROBE_ERR_INTEGRITY;
+    int dummy = 0;
+    std::vector<int> none;
+    if (world > 1 && rdv.allgather_fds(&dummy, 1, &none, &err) != -ENOTSUP) return CDPROBE_ERR_INTEGRITY;
+    return rdv.barrier(&err) == 0 ? CDPROBE_OK : CDPROBE_ERR_RENDEZVOUS;
+  }
   int fd = memfd_create("cdprobe-selftest", MFD_CLOEXEC);
   if (fd < 0) return CDPROBE_ERR_RENDEZVOUS;
   uint64_t words[64];

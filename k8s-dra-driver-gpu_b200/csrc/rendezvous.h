@@ -3,8 +3,10 @@
 //
 // A star over an abstract unix-domain socket named after the session: rank 0
 // is the hub.  It carries (a) cuMem POSIX file-descriptor handles via
-// SCM_RIGHTS, (b) small fixed-size blobs (mapping status, result rows) and
-// (c) a host barrier.  No data-path bytes travel here; the data path is
+// SCM_RIGHTS, (b) small fixed-size blobs (mapping status, fabric handles,
+// result rows) and (c) a host barrier.  A session of the form
+// "tcp:<host>:<port>" runs the same star over TCP — groundwork for cross-node
+// domains: blobs and the barrier only, never fds.  No data-path bytes travel here; the data path is
 // NVLink P2P between the mapped allocations.  NCCL is not used (north_star).
 #pragma once
 #include <stddef.h>
@@ -34,6 +36,7 @@ class Rendezvous {
 
   uint32_t rank() const { return rank_; }
   uint32_t world() const { return world_; }
+  bool is_tcp() const { return tcp_; }
 
  private:
   uint32_t rank_ = 0, world_ = 1;
@@ -41,6 +44,7 @@ class Rendezvous {
   int hub_fd_ = -1;              // client: connection to rank 0
   std::vector<int> client_fd_;   // hub: connection per rank (index 0 unused)
   uint32_t timeout_ms_ = 10000;
+  bool tcp_ = false;            // session "tcp:<host>:<port>": cross-node transport, blobs only
 };
 
 }  // namespace cdp

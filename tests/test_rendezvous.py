@@ -39,3 +39,28 @@ def test_missing_peer_times_out(pkg):
     rc = lib.cdprobe_rendezvous_selftest(f"t-{uuid.uuid4().hex[:12]}".encode(), 1, 2, 300)
     assert rc == pkg.abi.ERR_RENDEZVOUS
     assert lib.cdprobe_rendezvous_selftest(b"x", 3, 2, 100) == pkg.abi.ERR_ARG
+
+
+def _free_port():
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_tcp_transport_carries_blobs_not_fds(pkg, world):
+    """Cross-node groundwork (SURVEY §8f n4): a `tcp:<host>:<port>` session runs the same star over TCP;
+    blobs (what a CUmemFabricHandle is) and the barrier work, fd passing is refused."""
+    session = f"tcp:127.0.0.1:{_free_port()}"
+    procs = [subprocess.Popen([sys.executable, "-c", CHILD, session, str(r), str(world)]) for r in range(world)]
+    assert [p.wait(timeout=120) for p in procs] == [0] * world
+
+
+def test_tcp_session_syntax(pkg):
+    lib = pkg.abi.load_library()
+    assert lib.cdprobe_rendezvous_selftest(b"tcp:nohostport", 0, 2, 200) == pkg.abi.ERR_RENDEZVOUS
+    assert lib.cdprobe_rendezvous_selftest(f"tcp:127.0.0.1:{_free_port()}".encode(), 1, 2, 300) == pkg.abi.ERR_RENDEZVOUS
