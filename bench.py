@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA probe
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU/NVML poll
+    python bench.py --config c2|c3-full|c5 ...                # BASELINE configs 2 / 3 (full mode) / 5 (storm)
 
 A "step" is one pass of the hot path: one `cdprobe_run` over the N-GPU domain (sliced mode,
 1 GiB per GPU, read + write + verify) — BASELINE.json configs[2] at N GPUs; at N = 1 the same
@@ -35,7 +36,8 @@ if ROOT not in sys.path:
 
 GIB = 1 << 30
 NVLINK_PEAK_GBPS = 900.0        # nominal per direction per GPU
-NVLINK_MEASURED_GBPS = 770.0    # measured peer copy per direction (B200_PROFILING.md)
+NVLINK_GUIDE_CE_GBPS = 770.0    # the profiling guide's peer-copy figure; the line carries the SAME-BOX copy-engine
+                                # numbers measured next to the probe (roofline.peak_measured_ce_{uni,bidi})
 HBM_FALLBACK_GBPS = 6650.0
 
 
@@ -175,24 +177,26 @@ def run_reference(args):
         line["unavailable"] = f"NVML poll could not run: {e}"
         print(json.dumps(line))
         return 0
-    threaded = last.n > 1 and statistics.mean(tn) < statistics.mean(t1)
+    threaded = last.n > 1 and statistics.median(tn) < statistics.median(t1)
     times = tn if threaded else t1
     cores = last.n if threaded else 1
-    v = statistics.mean(times)
+    # the distribution has a 10-50x tail (first nvmlInit of a process, RM lock contention): the median is the
+    # typical poll, mean and max ride beside it
+    v = statistics.median(times)
     sample = (f"{len(times)} polls of the {last.n}-GPU node: nvmlInitWithFlags + enumerate + fabric info + "
               f"{18 * last.n} NvLinkState + {3 * last.n * (last.n - 1)} P2PStatus + nvmlShutdown "
               f"({last.nvml_calls} NVML calls per poll)")
     line.update({
-        "value": v, "ms_per_step": v, "steps": len(times), "warmup": args.warmup,
+        "value": v, "ms_per_step": statistics.mean(times), "steps": len(times), "warmup": args.warmup,
         "config": {"workload": workload_name(args.gpus, args.mode, args.bytes),
                    "reference_path": (f"the reference's CPU answer to the same question: NVML enumerate + NvLinkState + "
                                       f"P2PStatus poll of {last.n} GPU(s) -> N x N reachability matrix (it moves no bytes "
                                       f"and measures no bandwidth: SURVEY.md F1)"),
                    "n_gpus_polled": last.n, "threads": cores},
         "cpu_baseline": {"value": v, "unit": "ms", "cores": cores, "kind": "port", "sample": sample,
-                         "single_thread_ms": statistics.mean(t1), "thread_per_gpu_ms": statistics.mean(tn),
-                         "host_cores": os.cpu_count(), "median_ms": statistics.median(times),
-                         "max_ms": max(times),
+                         "single_thread_ms": statistics.median(t1), "thread_per_gpu_ms": statistics.median(tn),
+                         "host_cores": os.cpu_count(), "statistic": "median", "mean_ms": statistics.mean(times),
+                         "median_ms": statistics.median(times), "max_ms": max(times),
                          "phases_ms": {"init": last.init_ms, "enumerate": last.enumerate_ms, "fabric": last.fabric_ms,
                                        "link_poll": last.link_poll_ms, "p2p_poll": last.p2p_poll_ms,
                                        "shutdown": last.shutdown_ms}},
@@ -204,6 +208,57 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- our arm ----
+CONFIGS = {
+    # BASELINE.json configs[1]: 2-GPU P2P read/write reachability matrix, 64 MiB buffers, IMEX channel 0
+    "c2": {"gpus": 2, "bytes": 64 << 20, "mode": "full", "fabric": True,
+           "name": "BASELINE configs[1]: 2-GPU P2P read/write reachability matrix, 64 MiB buffers, full mode, "
+                   "fabric handles iff IMEX channel 0 exists"},
+    # configs[2] in full mode: every ordered pair moves the whole 1 GiB buffer (56 GiB over the fabric at N = 8)
+    "c3-full": {"gpus": None, "bytes": GIB, "mode": "full", "fabric": False,
+                "name": "BASELINE configs[2] in FULL mode: {n}-GPU all-pairs NVLink probe, 1 GiB per ordered pair"},
+    # configs[4]: reconcile storm — one probe per NodePrepare/Unprepare cycle, a peer mapping torn down and rebuilt each cycle
+    "c5": {"gpus": None, "bytes": GIB, "mode": "sliced", "fabric": False,
+           "name": "BASELINE configs[4]: reconcile storm, {cycles} prepare/unprepare cycles (unmap + remap of one peer, "
+                   "then a full probe) on {n} GPU(s)"},
+}
+
+
+def parity_block(pkg, oracle, res, n, nbytes, mode_id, uuids, seed):
+    """Driver-visible parity, outside every timed region: every cell's checksums against
+    the CPU oracle's restatement of the patterns, and reach_read AND reach_write against the reachability
+    matrix the oracle derives from the NVML poll (nvlib.go:208-363; go-nvml device.go:281-285,1652-1661),
+    matched by GPU UUID."""
+    diag = n == 1
+    cells = [(i, j) for i in range(n) for j in range(n) if i != j or diag]
+    bad = []
+    words = res.bytes_per_pair // 8
+    for i, j in cells:
+        exp_r = oracle.expected_read(seed, n, nbytes, mode_id, i, j, diag)
+        exp_w = oracle.write_checksum(seed, i, j, res.run_seq, words)
+        if (res.sum_read[i][j], res.xor_read[i][j]) != exp_r:
+            bad.append(["read", i, j])
+        if (res.sum_write[i][j], res.xor_write[i][j]) != exp_w:
+            bad.append(["write", i, j])
+    block = {"cells": len(cells), "checksum_ok": not bad, "checksum_mismatches": bad[:8],
+             "words_per_cell": words, "oracle": "oracle/pattern.c (scalar C restatement), oracle/nvml_poll.c"}
+    try:
+        o = oracle.nvml_poll()
+        by_uuid = {u: k for k, u in enumerate(o.uuids())}
+        idx = [by_uuid[u] for u in uuids]
+        om = o.reach_matrix()
+        exp = [[om[idx[i]][idx[j]] for j in range(n)] for i in range(n)]
+        block["reach_vs_nvml_ok"] = res.reach == exp
+        block["reach_cells_one"] = sum(sum(row) for row in res.reach)
+        block["nvml_gpus_polled"] = o.n
+        if res.reach != exp:
+            block["reach_mismatches"] = [[i, j, res.reach[i][j], exp[i][j]] for i in range(n) for j in range(n)
+                                         if res.reach[i][j] != exp[i][j]][:8]
+    except Exception as e:  # no NVML on the box: say so; never assume
+        block["reach_vs_nvml_ok"] = None
+        block["reach_vs_nvml_error"] = str(e)
+    return block
+
+
 def run_probe(args):
     import torch
 
@@ -212,6 +267,11 @@ def run_probe(args):
     pkg = cdprobe_pkg.load()
     abi = pkg.abi
     rank, world, local = dist_env()
+    conf = CONFIGS.get(args.config) if args.config else None
+    if conf:
+        args.bytes, args.mode = conf["bytes"], conf["mode"]
+        if conf["gpus"] and args.gpus != conf["gpus"]:
+            raise SystemExit(f"--config {args.config} is defined on {conf['gpus']} GPUs (launch with --gpus {conf['gpus']})")
     if world == 1 and args.gpus > 1:
         raise SystemExit("launch N > 1 with torchrun: one process per GPU")
     n = args.gpus
@@ -219,7 +279,6 @@ def run_probe(args):
     if torch.cuda.device_count() <= local:
         local = 0
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     grp = pkg.distutil.RankGroup(backend="gloo")  # host-side only: barrier + max; the data path uses no collective library
 
     def barrier():
@@ -230,17 +289,40 @@ def run_probe(args):
 
     session = grp.session()
     flags = abi.FLAG_PATH_LDST if args.path == "ldst" else 0
-    cfg = pkg.Config(ordinals=[local], bytes=args.bytes, mode={"sliced": 1, "full": 2, "reach": 0}[args.mode],
-                     ops=3, flags=flags, ctas=args.ctas, world_size=world, rank=rank, session=session,
-                     timeout_ms=args.timeout_ms)
+    if conf and conf["fabric"]:
+        flags |= abi.FLAG_FABRIC_HANDLES
+    if args.all_rank_barriers:
+        flags |= abi.FLAG_ALL_RANK_BARRIERS
+    mode_id = {"sliced": 1, "full": 2, "reach": 0}[args.mode]
+    cfg = pkg.Config(ordinals=[local], bytes=args.bytes, mode=mode_id, ops=3, flags=flags, ctas=args.ctas,
+                     world_size=world, rank=rank, session=session, timeout_ms=args.timeout_ms)
+    # what a daemon pod pays before its first verdict: contexts + VMM + mapping + fill + source checksums (open),
+    # then one cold probe.  Wall clock around the public calls, max over ranks.
+    barrier()
+    t_open0 = time.perf_counter()
     probe = pkg.Open(cfg)
-    info = probe.Info()
+    t_open1 = time.perf_counter()
     out = abi.ResultT()
 
     def step():
         rc = probe.run_raw(out)
         if rc != abi.OK:
             raise RuntimeError(f"cdprobe_run rc={rc}: {abi.load_library().cdprobe_last_error().decode()}")
+
+    step()
+    t_first = time.perf_counter()
+    info = probe.Info()
+    daemon_cost = {
+        "open_call_ms": max_over_ranks((t_open1 - t_open0) * 1e3),
+        "open_ms": max_over_ranks(info.open_ms), "fill_and_checksum_ms": max_over_ranks(info.fill_ms),
+        "first_run_ms": max_over_ranks((t_first - t_open1) * 1e3),
+        "cold_first_verdict_ms": max_over_ranks((t_first - t_open0) * 1e3),
+        "note": "cdprobe_open (CUDA contexts, cuMemCreate/Map of every rank's buffer, pattern fill, source "
+                "checksums, rendezvous) + the first cdprobe_run; the steady-state `value`/`e2e` exclude it",
+    }
+
+    if args.config == "c5":
+        return run_storm(args, pkg, probe, grp, info, n, rank, local, daemon_cost, conf)
 
     # ---- warm-up (untimed) --------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -253,7 +335,7 @@ def run_probe(args):
     # ---- loop A: kernel durations by CUDA events on the launch stream -> `value`, roofline
     probe.SetOption(abi.OPT_EVENT_TIMING, 1)
     step()
-    ev, dev_ms, rd, wr = [], [], [], []
+    ev, dev_ms, rd, wr, bar_us = [], [], [], [], []
     barrier()
     for _ in range(args.steps):
         step()
@@ -261,6 +343,7 @@ def run_probe(args):
         dev_ms.append(out.device_ms[0])
         rd.append(out.min_gbps_read)
         wr.append(out.min_gbps_write)
+        bar_us.append(out.barrier_us[0])
     barrier()
     probe.SetOption(abi.OPT_EVENT_TIMING, 0)
 
@@ -285,6 +368,7 @@ def run_probe(args):
     value = max_over_ranks(statistics.mean(ev))
     device_ms = max_over_ranks(statistics.mean(dev_ms))
     e2e_ms = max_over_ranks(statistics.mean(host_ms))
+    barrier_us = max_over_ranks(statistics.median(bar_us))
 
     # per-pair GB/s over the whole domain: the last timed step's rows, completed across ranks
     rc = abi.load_library().cdprobe_gather(probe._h, ctypes.byref(out))
@@ -292,6 +376,17 @@ def run_probe(args):
         raise RuntimeError(f"cdprobe_gather rc={rc}")
     res = pkg.Result.from_c(out)
     warmed_steps = max_over_ranks(float(warmed))
+
+    # ---- parity self-check (untimed, every N): rank 0 holds the gathered matrices ----------------
+    uuids = grp.gather_objects(info.uuid[0].value.decode())
+    parity = None
+    if rank == 0:
+        from oracle import oracle as o  # the checker: never on the measured path
+
+        o.build()
+        parity = parity_block(pkg, o, res, n, args.bytes, mode_id, uuids, o.DEFAULT_SEED)
+    parity_ok = grp.gather_objects(None if parity is None else
+                                   bool(parity["checksum_ok"] and parity["reach_vs_nvml_ok"] is not False))[0]
 
     # the daemon's situation: ONE probe after the GPUs sat idle (NVLink leaves its active state);
     # the library's automatic wake-up phase is part of this number
@@ -306,6 +401,7 @@ def run_probe(args):
     pairs_r = [res.gbps_read[i][j] for i in range(n) for j in range(n) if i != j or n == 1]
     pairs_w = [res.gbps_write[i][j] for i in range(n) for j in range(n) if i != j or n == 1]
     reach_ok = all(res.reach[i][j] == 1 for i in range(n) for j in range(n))
+
     def pct(v, f):
         v = sorted(v)
         return v[min(len(v) - 1, max(0, int(round(f * (len(v) - 1)))))]
@@ -321,6 +417,7 @@ def run_probe(args):
     # per-link figure with one-way payload (each ordered pair alone on its two ports): a few extra,
     # untimed-for-the-headline runs with the unidirectional schedule
     uni = None
+    ce = None
     if n > 1:
         probe.SetOption(abi.OPT_UNIDIRECTIONAL, 1)
         for _ in range(2):
@@ -332,8 +429,23 @@ def run_probe(args):
         uni = {"read_min": min(u_r), "read_median": statistics.median(u_r), "write_min": min(u_w),
                "write_median": statistics.median(u_w), "probe_ms": statistics.median(u.probe_ms for u in ur),
                "frac_min_of_900": min(min(u_r), min(u_w)) / NVLINK_PEAK_GBPS,
-               "frac_min_of_measured_770": min(min(u_r), min(u_w)) / NVLINK_MEASURED_GBPS,
                "reach_all_ones": all(all(all(c == 1 for c in row) for row in u.reach) for u in ur)}
+        # ---- the same-box ceiling: the copy engine on the very same buffers, ranks 0 <-> 1 (untimed for the
+        # headline).  One way: rank 0 pushes alone.  Both ways: ranks 0 and 1 push to each other at once (each
+        # process enqueues `reps` back-to-back copies after a host barrier; ~10 ms of copy hides the skew).
+        reps = 8
+        barrier()
+        uni_push = probe.CeCopy([(0, 1)], push=True, reps=reps)[0][1] if rank == 0 else 0.0
+        barrier()
+        uni_pull = probe.CeCopy([(0, 1)], push=False, reps=reps)[0][1] if rank == 0 else 0.0
+        barrier()
+        bidi = probe.CeCopy([(0, 1 - rank)], push=True, reps=reps)[0][1] if rank < 2 else 1e30
+        barrier()
+        ce = {"uni_push": max_over_ranks(uni_push), "uni_pull": max_over_ranks(uni_pull), "bidi_push_min": grp.min(bidi),
+              "bytes_per_copy": min(bpp * (n - 1), args.bytes if args.mode != "full" else bpp), "copies": reps,
+              "how": "cudaMemcpyAsync (copy engine) between rank 0's and rank 1's probe buffers, CUDA events on the "
+                     "issuing rank's stream; bidi = both ranks pushing at once"}
+        uni["frac_min_of_ce_uni"] = min(min(u_r), min(u_w)) / max(ce["uni_push"], ce["uni_pull"])
 
     peaks, peak_kind = measured_peaks()
     passes = 3  # read B, write B, verify B per GPU per probe
@@ -360,27 +472,35 @@ def run_probe(args):
         link_achieved = min(min(pairs_r), min(pairs_w))
         roofline = {"bound": "nvlink", "achieved": link_achieved, "peak": NVLINK_PEAK_GBPS, "unit": "GB/s",
                     "frac": link_achieved / NVLINK_PEAK_GBPS, "traffic": None,
-                    "peak_kind": "nominal NVLink 5 per direction per GPU (measured peer copy: 770 GB/s)",
-                    "frac_of_measured_770": link_achieved / NVLINK_MEASURED_GBPS,
+                    "peak_kind": "nominal NVLink 5 per direction per GPU; the same-box copy-engine ceilings are beside it",
+                    "peak_measured_ce_uni": max(ce["uni_push"], ce["uni_pull"]), "peak_measured_ce_bidi": ce["bidi_push_min"],
+                    "frac_of_ce_bidi": link_achieved / ce["bidi_push_min"],
+                    "frac_read_of_ce_bidi": min(pairs_r) / ce["bidi_push_min"],
+                    "frac_write_of_ce_bidi": min(pairs_w) / ce["bidi_push_min"],
+                    "ce": ce,
                     "kernel": "cdprobe_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                     "nvlink_bytes_per_launch_per_direction": a_gpu,
                     "aggregate_link_gbps_per_gpu": link_bytes / (value * 1e-3) / 1e9,
-                    "note": "achieved = slowest ordered pair with exclusive endpoints (tournament round)"}
+                    "note": "achieved = slowest ordered pair with exclusive endpoints (tournament round), both "
+                            "directions of every port loaded; SM-issued peer stores cap at ~715 GB/s one way on "
+                            "every store shape (profiles/r02_linkbench_n2.jsonl)"}
 
     if rank == 0:
+        wl = conf["name"].format(n=n, cycles=0) if conf else workload_name(n, args.mode, args.bytes)
         line = {
             "metric": "nvlink_probe_ms", "value": value, "unit": "ms", "n_gpus": n, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {
-                "workload": workload_name(n, args.mode, args.bytes),
+                "workload": wl, "config": args.config or "c3-sliced",
                 "bytes_per_gpu": args.bytes, "bytes_per_pair": bpp, "mode": args.mode, "path": args.path,
                 "ctas": int(info.ctas[0]), "rounds": res.rounds, "phases": res.phases,
+                "barriers": "all-rank" if args.all_rank_barriers else "neighbourhood",
                 "parallelism": f"{n} ranks, one process per GPU, no data-path collective",
                 "l2": "inputs (1 GiB per pass) exceed the 126 MB L2; no explicit flush",
                 "handle_type": int(info.handle_type),
             },
-            "device_ms_globaltimer": device_ms,
+            "device_ms_globaltimer": device_ms, "barrier_us": barrier_us,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 2768,
                     "d2h_bytes_per_step": 32 + 120 * int(res.phases),
                     "note": "cdprobe_run from a host thread: kernel parameters (2768 B) in, result row "
@@ -394,12 +514,14 @@ def run_probe(args):
                 "frac_min": min(min(pairs_r), min(pairs_w)) / (NVLINK_PEAK_GBPS if n > 1 else peaks["hbm_gbs"]),
                 "run_to_run_spread_read": spread_r, "run_to_run_spread_write": spread_w,
                 "worst_step_drop_read": worst_r, "worst_step_drop_write": worst_w, "probe_ms_spread": ev_spread,
+                "gate_gbps_read": res.gate_gbps_read, "gate_gbps_write": res.gate_gbps_write,
             },
             "job_throughput_gbps": (n * passes * a_gpu / (value * 1e-3) / 1e9) if n == 1 else
                                    (n * 2 * a_gpu / (value * 1e-3) / 1e9),
             "job_throughput_note": "whole-job bytes per probe / probe time: N x (read + write) payload over NVLink "
                                    "(N = 1: read + write + verify through HBM)",
             "reachability_all_ones": reach_ok, "verdict": bool(res.verdict),
+            "parity": parity, "daemon_cost": daemon_cost,
             "cold_start": cold_start, "timed_steps_with_wakeup_phase_traffic": warmed_steps,
             "roofline": roofline, "clocks": clocks,
         }
@@ -412,26 +534,123 @@ def run_probe(args):
                 "note": "NVML fields 138/139 (NVLink data TX/RX KiB) on rank 0's GPU across both timed loops "
                         "(2 x steps + 2 probes); per probe each direction carries the write payload and the "
                         "read responses: 2 x (N-1) x bytes_per_pair"}
-        if n == 1 and not args.no_cpu_baseline:
-            # fresh process, as the reference's `check` is exec'ed per kubelet probe (NVML init is not
-            # amortised): the reference arm of this same script, bounded to ~20 polls
-            try:
-                import subprocess
-
-                env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
-                cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", "1",
-                                     "--steps", "20", "--warmup", "2"], capture_output=True, text=True, timeout=120,
-                                    env=env)
-                ref = json.loads([l for l in cp.stdout.splitlines() if l.startswith("{")][-1])
-                line["cpu_baseline"] = ref.get("cpu_baseline") or {"value": None, "unit": "ms", "cores": 1,
-                                                                     "kind": "port", "sample": ref.get("unavailable")}
-            except Exception as e:
-                line["cpu_baseline"] = {"value": None, "unit": "ms", "cores": 1, "kind": "port",
-                                        "sample": f"unavailable: {e}"}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_subprocess(n)
         print(json.dumps(line))
     probe.Close()
     grp.close()
+    if parity_ok is False:
+        if rank == 0:
+            sys.stderr.write("PARITY FAILURE: " + json.dumps(parity) + "\n")
+        return 3
     return 0
+
+
+def cpu_baseline_subprocess(n: int):
+    """The reference's CPU path in a fresh process (its `check` is exec'ed per kubelet probe: NVML init is never
+    amortised), bounded to ~10-20 polls: the reference arm of this same script."""
+    try:
+        import subprocess
+
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        steps = 20 if n == 1 else 8
+        cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--gpus", str(n),
+                             "--steps", str(steps), "--warmup", "2"], capture_output=True, text=True, timeout=180, env=env)
+        ref = json.loads([l for l in cp.stdout.splitlines() if l.startswith("{")][-1])
+        return ref.get("cpu_baseline") or {"value": None, "unit": "ms", "cores": 1, "kind": "port",
+                                           "sample": ref.get("unavailable")}
+    except Exception as e:
+        return {"value": None, "unit": "ms", "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
+
+
+def run_storm(args, pkg, probe, grp, info, n, rank, local, daemon_cost, conf):
+    """BASELINE configs[4]: `--steps` prepare/unprepare cycles on one open handle; every cycle
+    tears down and rebuilds this rank's mapping of one peer (the NodeUnprepare/NodePrepare churn a live domain
+    sees, cmd/compute-domain-kubelet-plugin/driver.go:165-232) and then runs a full probe.  Reports p50/p99 per
+    cycle, device memory and fd deltas (leak check), and the parity block of the LAST cycle."""
+    import torch
+
+    abi = pkg.abi
+    cycles = args.steps
+    out = abi.ResultT()
+
+    def fd_count():
+        try:
+            return len(os.listdir("/proc/self/fd"))
+        except OSError:
+            return -1
+
+    def cycle(k):
+        t0 = time.perf_counter()
+        if n > 1:
+            peer = (rank + 1 + k % (n - 1)) % n
+            probe.RemapPeer(0, peer)
+        t1 = time.perf_counter()
+        rc = probe.run_raw(out)
+        if rc != abi.OK:
+            raise RuntimeError(f"cycle {k}: cdprobe_run rc={rc}: {abi.load_library().cdprobe_last_error().decode()}")
+        t2 = time.perf_counter()
+        return (t1 - t0) * 1e3, (t2 - t1) * 1e3, bool(out.verdict), out.min_gbps_read, out.min_gbps_write
+
+    for k in range(max(args.warmup, 3)):
+        cycle(k)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    fds0 = fd_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    grp.barrier()
+    t0 = time.perf_counter()
+    rows = [cycle(k) for k in range(cycles)]
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    grp.barrier()
+    clocks = sampler.stop()
+    free1, _ = torch.cuda.mem_get_info()
+    fds1 = fd_count()
+
+    def pct(v, f):
+        v = sorted(v)
+        return v[min(len(v) - 1, max(0, int(round(f * (len(v) - 1)))))]
+
+    cyc = [a + b for a, b, *_ in rows]
+    probe_ms = [b for _, b, *_ in rows]
+    remap_ms = [a for a, *_ in rows]
+    stats = {"cycles": cycles, "wall_ms": grp.max(wall),
+             "cycle_ms_p50": grp.max(pct(cyc, 0.5)), "cycle_ms_p99": grp.max(pct(cyc, 0.99)), "cycle_ms_max": grp.max(max(cyc)),
+             "probe_ms_p50": grp.max(pct(probe_ms, 0.5)), "probe_ms_p99": grp.max(pct(probe_ms, 0.99)),
+             "remap_ms_p50": grp.max(pct(remap_ms, 0.5)), "remap_ms_p99": grp.max(pct(remap_ms, 0.99)),
+             "verdict_failures": int(grp.max(float(sum(1 for r in rows if not r[2])))),
+             "read_min_gbps": grp.min(min(r[3] for r in rows)), "write_min_gbps": grp.min(min(r[4] for r in rows)),
+             "device_free_delta_bytes": int(grp.max(float(abs(free0 - free1)))), "fd_delta": int(grp.max(float(abs(fds1 - fds0))))}
+    rc = abi.load_library().cdprobe_gather(probe._h, ctypes.byref(out))
+    if rc != abi.OK:
+        raise RuntimeError(f"cdprobe_gather rc={rc}")
+    res = pkg.Result.from_c(out)
+    uuids = grp.gather_objects(info.uuid[0].value.decode())
+    parity = None
+    if rank == 0:
+        from oracle import oracle as o
+
+        o.build()
+        parity = parity_block(pkg, o, res, n, args.bytes, 1, uuids, o.DEFAULT_SEED)
+        line = {"metric": "nvlink_probe_ms", "value": stats["probe_ms_p50"], "unit": "ms", "n_gpus": n, "steps": cycles,
+                "warmup": max(args.warmup, 3), "ms_per_step": stats["wall_ms"] / cycles, "higher_is_better": False,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": conf["name"].format(n=n, cycles=cycles), "config": "c5", "bytes_per_gpu": args.bytes,
+                           "bytes_per_pair": res.bytes_per_pair, "mode": "sliced",
+                           "parallelism": f"{n} ranks, one process per GPU, no data-path collective"},
+                "e2e": {"value": stats["cycle_ms_p50"], "unit": "ms", "h2d_bytes_per_step": 2768,
+                        "d2h_bytes_per_step": 32 + 120 * int(res.phases),
+                        "note": "one reconcile cycle through the public ABI: cdprobe_remap_peer + cdprobe_run (p50)"},
+                "gpu_launches": cycles * n, "storm": stats, "parity": parity, "daemon_cost": daemon_cost,
+                "reachability_all_ones": all(all(c == 1 for c in row) for row in res.reach), "verdict": bool(res.verdict),
+                "clocks": clocks}
+        print(json.dumps(line))
+    ok = grp.gather_objects(None if parity is None else bool(parity["checksum_ok"] and parity["reach_vs_nvml_ok"] is not False))[0]
+    probe.Close()
+    grp.close()
+    return 3 if ok is False else 0
 
 
 def main():
@@ -446,6 +665,10 @@ def main():
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--timeout-ms", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="", choices=["", "c2", "c3-full", "c5"],
+                    help="BASELINE.json configs beyond the headline: c2 (2 GPUs, 64 MiB, full), c3-full (1 GiB per ordered "
+                         "pair), c5 (reconcile storm: --steps cycles)")
+    ap.add_argument("--all-rank-barriers", action="store_true", help="round-1 barrier schedule (comparison)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -40,7 +40,7 @@ extern "C" {
 #define CDPROBE_API
 #endif
 
-#define CDPROBE_ABI_VERSION 1u
+#define CDPROBE_ABI_VERSION 2u         /* 2: neighbourhood barriers (sync_mask), calibrated gate, ce_copy */
 #define CDPROBE_MAX_GPUS 16          /* ranks in one probe domain (8 on HGX B200) */
 #define CDPROBE_MAX_PHASES 64
 #define CDPROBE_NVLINK_MAX_LINKS 18  /* == NVML_NVLINK_MAX_LINKS (nvml.h:389) */
@@ -77,6 +77,9 @@ extern "C" {
 #define CDPROBE_FLAG_SIMULATE_MIG 0x200u   /* treat every local GPU as a MIG instance (BASELINE config 4 without MIG hardware) */
 #define CDPROBE_FLAG_SERIAL_VERIFY 0x100u  /* opt out of the overlapped verify: verify every slot after the rounds */
 #define CDPROBE_FLAG_ALLOW_SAME_DEVICE 0x40u /* several ranks may name the same CUDA ordinal (testing) */
+#define CDPROBE_FLAG_ALL_RANK_BARRIERS 0x400u /* every tournament phase closes with an all-rank flag exchange (round-1
+                                              behaviour); default: only the ranks whose traffic shares an NVLink
+                                              port with this rank's in the two phases either side of the barrier */
 #define CDPROBE_FLAG_UNIDIRECTIONAL 0x80u  /* each round in two halves: one rank of a pair issues at a time, so a
                                               port carries payload one way only (per-link figure; 2x the phases) */
 
@@ -92,12 +95,19 @@ typedef struct {
   uint32_t timeout_ms;                  /* device + host watchdog; 0 = 5000 */
   uint32_t flags;                       /* CDPROBE_FLAG_* */
   uint64_t seed;                        /* 0 = 0xCD5EED0000000001 */
-  float min_fraction;                   /* verdict threshold on pair GB/s / link_peak; 0 = 0.65 (10 % under the measured
-                                           healthy floor of 0.72 at 1 GiB per GPU).  The north_star's
-                                           0.85 is not a safe gate: a healthy B200 port measures 0.73-0.78 of 900 GB/s
-                                           with both directions loaded and 0.84-0.86 (reads) / 0.77-0.79 (writes) one
-                                           way, so 0.85 would mark healthy nodes NotReady. */
-  float link_peak_gbps;                 /* 0 = 900 (NVLink 5, per direction per GPU) */
+  float min_fraction;                   /* verdict threshold on pair GB/s, as a fraction of the reference figure below;
+                                           0 = default (0.90 with the calibrated reference, see link_peak_gbps) */
+  float link_peak_gbps;                 /* reference figure of the gate.
+                                           0 (default) = CALIBRATED: what a healthy B200 NVLink-5 port delivers to
+                                           SM-issued traffic of that op and schedule, measured next to the copy engine
+                                           on the same box (profiles/r02_linkbench_n2.jsonl: both directions loaded,
+                                           reads 672 / writes 703 GB/s; one way, reads 785 / writes 714.7 — SM stores
+                                           cap there on every store shape and CTA count; the copy engine moves
+                                           773-778), de-rated for the ~8 us a phase spends ramping and draining:
+                                               expected(bytes_per_pair) = bytes_per_pair / (bytes_per_pair / rate + 8 us)
+                                           >0 = absolute: threshold = min_fraction x link_peak_gbps (900 = nominal
+                                           NVLink 5 per direction; the north_star's "0.85 x 900 = 765" is above what
+                                           any SM write and any bidirectional transfer reaches on healthy hardware) */
   uint32_t ctas;                        /* CTAs of the persistent kernel; 0 = one per SM */
   uint32_t world_size;                  /* processes in the probe domain; 0/1 = single process */
   uint32_t rank;                        /* this process's index in [0, world_size) */
@@ -137,6 +147,10 @@ typedef struct {
                                            (only with CDPROBE_OPT_EVENT_TIMING; 0 otherwise) */
   float min_gbps_read;                  /* over filled off-diagonal cells (diagonal when n == 1) */
   float min_gbps_write;
+  float gate_gbps_read;                 /* the GB/s threshold this run's verdict applied to reads (0: bandwidth not judged) */
+  float gate_gbps_write;
+  uint32_t unreachable_pairs;           /* filled off-diagonal cells with reach_read & reach_write == 0 (MIG-excluded cells not counted) */
+  uint32_t slow_pairs;                  /* filled off-diagonal cells that are reachable but under the gate */
 } cdprobe_result_t;
 
 typedef struct {
@@ -182,6 +196,7 @@ typedef struct {
   uint8_t kind0[CDPROBE_MAX_PHASES], kind1[CDPROBE_MAX_PHASES];  /* 0 none, 1 read, 2 write, 3 verify, 4 warm-up */
   int8_t peer0[CDPROBE_MAX_PHASES], peer1[CDPROBE_MAX_PHASES];
   uint8_t sync_all[CDPROBE_MAX_PHASES];                          /* closing barrier spans all ranks */
+  uint16_t sync_mask[CDPROBE_MAX_PHASES];                        /* ranks of the closing barrier's flag exchange */
   uint64_t t_start[CDPROBE_MAX_PHASES];                          /* opening barrier released */
   uint64_t t_end0[CDPROBE_MAX_PHASES], t_end1[CDPROBE_MAX_PHASES]; /* last CTA of job 0 / job 1 done */
   uint64_t t_arrive[CDPROBE_MAX_PHASES];                         /* every local CTA reached the closing barrier */
@@ -199,6 +214,7 @@ typedef struct {
   uint8_t writer[2][CDPROBE_MAX_PHASES];           /* verify: the rank that wrote the slot */
   uint16_t cta0[2][CDPROBE_MAX_PHASES], nctas[2][CDPROBE_MAX_PHASES];
   uint8_t sync_all[CDPROBE_MAX_PHASES];            /* closing barrier spans all ranks */
+  uint16_t sync_mask[CDPROBE_MAX_PHASES];          /* ranks this rank exchanges flags with when the phase closes */
 } cdprobe_schedule_t;
 
 /* Node topology as NVML reports it (no CUDA; internal/common topology enumeration). */
@@ -236,7 +252,7 @@ CDPROBE_API const char* cdprobe_last_error(void);
  *   cdprobe_remap_peer / cdprobe_unmap_peer  emulate NodeUnprepare/NodePrepare churn around a live domain:
  *                                                                   cmd/compute-domain-kubelet-plugin/driver.go:165-232
  *   cdprobe_gather, cdprobe_info, cdprobe_trace, cdprobe_set_option, cdprobe_corrupt, cdprobe_plan,
- *   cdprobe_schedule, cdprobe_rendezvous_selftest: diagnostics, benches, fault injection; the reference has
+ *   cdprobe_schedule, cdprobe_ce_copy, cdprobe_rendezvous_selftest: diagnostics, benches, fault injection; the reference has
  *   no counterpart (it has no probe).
  */
 CDPROBE_API int cdprobe_open(const cdprobe_config_t* cfg, cdprobe_t** out);
@@ -256,7 +272,21 @@ CDPROBE_API int cdprobe_trace(cdprobe_t* h, uint32_t local, cdprobe_trace_t* out
 #define CDPROBE_OPT_WARMUP 8u        /* link wake-up phase: 0 never, 1 auto = after > 5 ms idle (default), 2 always */
 #define CDPROBE_OPT_DEBUG_SKIP_RANK 10u /* fault injection: 1-based local rank whose kernel is not launched (0 = off) */
 #define CDPROBE_OPT_WARMUP_BYTES 9u  /* bytes each rank streams from its first partner when warming (default 8 MiB, capped at bytes_per_pair) */
+#define CDPROBE_OPT_CTAS_RANK 11u    /* value = ((local rank + 1) << 16) | ctas: CTA count of ONE local rank (tests: a throttled issuer) */
+#define CDPROBE_OPT_MIN_FRACTION_PPM 12u /* min_fraction x 1e6 (0 = default) */
+#define CDPROBE_OPT_LINK_PEAK_MBPS 13u   /* link_peak_gbps x 1e3 (0 = calibrated reference) */
+#define CDPROBE_OPT_SOLO_RANK 14u    /* profiling: 1-based local rank that runs ALONE — only its own read/write jobs, no
+                                        cross-GPU barrier, nobody verifies its writes (reach_write stays 0).  A single
+                                        self-contained kernel is what `ncu` can replay: NVLink byte counters per launch. */
+#define CDPROBE_OPT_ALL_RANK_BARRIERS 15u /* value 0/1: see CDPROBE_FLAG_ALL_RANK_BARRIERS */
 CDPROBE_API int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value);
+/* Copy-engine reference on the probe's own buffers (the same-box ceiling the roofline is quoted against; not part
+ * of a probe): copy k moves `bytes` (capped at the source / landing size) `reps` times back to back between local
+ * rank local[k] and rank peer[k] — push != 0: local source -> peer landing area, else peer source -> local landing
+ * area — on local[k]'s stream.  All n_copies are enqueued before any is waited for (bidirectional: two copies in
+ * one call, or one call per process after a host barrier).  ms_out[k] = CUDA-event time of copy k's `reps` copies. */
+CDPROBE_API int cdprobe_ce_copy(cdprobe_t* h, uint32_t n_copies, const uint32_t* local, const uint32_t* peer, uint32_t push,
+                                uint64_t bytes, uint32_t reps, double* ms_out);
 /* Storm/unprepare emulation: unmap + remap rank `peer` in local rank `local`'s address space. */
 CDPROBE_API int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer);
 /* Fault injection for parity tests: drop local rank's mapping of `peer` (cell becomes unreachable, run still returns). */

@@ -1,16 +1,24 @@
 // fabricprobe.go — new file for cmd/compute-domain-daemon (NVIDIA/k8s-dra-driver-gpu).
 //
 // NOT COMPILED IN THIS REPOSITORY (no Go toolchain in the build image, SURVEY.md F4).  The behaviour
-// it specifies is executable as the C++ mirror k8s-dra-driver-gpu_b200/csrc/daemon_main.cc
-// (`cdprobe-daemon {run,check}`, tests/test_daemon.py).
+// it specifies is executable as the C++ twin k8s-dra-driver-gpu_b200/csrc/daemon_main.cc
+// (`cdprobe-daemon {run,check}`, tests/test_daemon.py).  The two share ONE verdict file schema:
+// tests/test_daemon.py parses the json tags of fabricProbeVerdict below and checks every key and JSON
+// type of the file the C++ twin writes against them, so either `run` can feed either `check`.
 //
-// Wiring (two call sites in main.go, see INTEGRATION.md §2):
+// Wiring (INTEGRATION.md §2 has the main.go hunks):
 //   run():   after addComputeDomainCliqueLabel(), BEFORE the `if flags.cliqueID == ""` early wait
 //            (main.go:244-250) so single-node HGX boxes are covered too:
-//                stopProbe := startFabricProbe(ctx, flags, controllerUpdates)
-//                defer stopProbe()
-//   check(): after the existing IMEX gate (main.go:435-459):
-//                if err := checkFabricProbeVerdict(); err != nil { return err }
+//                prober := startFabricProbe(ctx, flags)
+//                defer prober.Stop()
+//   update loops (main.go:351-431): the probe is re-run from INSIDE the existing loops, after
+//            writeDaemonsConfig / UpdateDNSNameMappings:
+//                prober.Kick()
+//            GetDaemonInfoUpdateChan() keeps its single receiver — a second `range` over that channel
+//            would steal daemon-set updates from the IMEX config / DNS loops (a Go channel delivers each
+//            value to exactly one receiver).
+//   check(): after the existing IMEX gate (main.go:435-459), and in its cliqueID == "" early return:
+//                if err := checkFabricProbeVerdict(flags); err != nil { return err }
 package main
 
 import (
@@ -20,105 +28,202 @@ import (
 	"fmt"
 	"os"
 	"path/filepath"
+	"strings"
 	"time"
 
 	"k8s.io/klog/v2"
 
 	"sigs.k8s.io/dra-driver-nvidia-gpu/pkg/fabricprobe"
 	"sigs.k8s.io/dra-driver-nvidia-gpu/pkg/featuregates"
+	"sigs.k8s.io/dra-driver-nvidia-gpu/pkg/metrics"
 )
 
 const (
-	// The per-ComputeDomain bind mount shared by `run` and `check` (computedomain.go:170-177).
-	fabricProbeVerdictPath = "/imexd/fabricprobe.json"
+	// The per-ComputeDomain bind mount shared by `run` and `check` (computedomain.go:170-177).  It is a
+	// host path that outlives pods: run() removes whatever verdict it finds there before probing, and
+	// every verdict names the pod and boot that wrote it.
+	fabricProbeVerdictPath   = "/imexd/fabricprobe.json"
+	fabricProbeVerdictSchema = 2
 )
 
+// fabricProbeVerdict is the file `run` writes and `check` reads.  Reach matrices are 0/1 integers
+// (a []bool would marshal as true/false and a []uint8 as base64; the C++ twin prints integers).
 type fabricProbeVerdict struct {
+	Schema           int       `json:"schema"`
 	TimeUnix         int64     `json:"time_unix"`
+	PodUID           string    `json:"pod_uid"`
+	BootID           string    `json:"boot_id"`
 	OK               bool      `json:"ok"`
 	N                int       `json:"n"`
 	UnreachablePairs int       `json:"unreachable_pairs"`
+	SlowPairs        int       `json:"slow_pairs"`
 	MinGBpsRead      float32   `json:"min_gbps_read"`
 	MinGBpsWrite     float32   `json:"min_gbps_write"`
+	GateGBpsRead     float32   `json:"gate_gbps_read"`
+	GateGBpsWrite    float32   `json:"gate_gbps_write"`
 	ProbeMs          float64   `json:"probe_ms"`
-	ReachRead        []bool    `json:"reach_read"`
-	ReachWrite       []bool    `json:"reach_write"`
+	BytesPerPair     uint64    `json:"bytes_per_pair"`
+	ReachRead        []int     `json:"reach_read"`
+	ReachWrite       []int     `json:"reach_write"`
 	GBpsRead         []float32 `json:"gbps_read"`
 	GBpsWrite        []float32 `json:"gbps_write"`
 	Error            string    `json:"error"`
 }
 
-// startFabricProbe opens the probe once and re-runs it whenever the set of daemons in the domain
-// changes (the same signal that drives IMEXDaemonUpdateLoopWithDNSNames, main.go:384-431).
-func startFabricProbe(ctx context.Context, flags *Flags, updates <-chan struct{}) (stop func()) {
-	stop = func() {}
-	if !featuregates.Enabled(featuregates.FabricProbe) {
-		return stop
+// fabricProber owns the probe handle.  Kick() asks for another pass and never blocks: the update
+// loops call it from their own goroutine.
+type fabricProber struct {
+	kick chan struct{}
+	done chan struct{}
+}
+
+func (p *fabricProber) Kick() {
+	if p == nil || p.kick == nil {
+		return
 	}
-	probe, err := fabricprobe.Open(fabricprobe.Config{
-		Bytes:       flags.fabricProbeBytes,       // FABRIC_PROBE_BYTES, default 1 GiB
-		Mode:        flags.fabricProbeMode,        // FABRIC_PROBE_MODE, default sliced
-		MinFraction: flags.fabricProbeMinFraction, // FABRIC_PROBE_MIN_FRACTION, 0 = library default
-		Flags:       fabricprobe.FlagFabricHandles | fabricprobe.FlagMigAware,
-	})
+	select {
+	case p.kick <- struct{}{}:
+	default: // a pass is already pending
+	}
+}
+
+func (p *fabricProber) Stop() {
+	if p == nil || p.done == nil {
+		return
+	}
+	<-p.done
+}
+
+func bootID() string {
+	raw, err := os.ReadFile("/proc/sys/kernel/random/boot_id")
+	if err != nil {
+		return ""
+	}
+	return strings.TrimSpace(string(raw))
+}
+
+func boolsToInts(b []bool) []int {
+	out := make([]int, len(b))
+	for i, v := range b {
+		if v {
+			out[i] = 1
+		}
+	}
+	return out
+}
+
+// startFabricProbe removes a stale verdict, opens the probe and runs it once; further passes happen on
+// Kick() (daemon-set changes) and every flags.fabricProbeInterval when that is set.  It returns at
+// once; Stop() waits for the goroutine (which exits on ctx cancel) and closes the handle.
+func startFabricProbe(ctx context.Context, flags *Flags) *fabricProber {
+	p := &fabricProber{}
+	if !featuregates.Enabled(featuregates.FabricProbe) {
+		return p
+	}
+	// Whatever is in the mount was written by another pod / container instance.
+	if err := os.Remove(fabricProbeVerdictPath); err != nil && !errors.Is(err, os.ErrNotExist) {
+		klog.Warningf("cannot remove stale %s: %v", fabricProbeVerdictPath, err)
+	}
+	cfg := fabricprobe.Config{
+		Bytes:        flags.fabricProbeBytes,       // FABRIC_PROBE_BYTES, default 1 GiB
+		Mode:         flags.fabricProbeMode,        // FABRIC_PROBE_MODE, default sliced
+		MinFraction:  flags.fabricProbeMinFraction, // FABRIC_PROBE_MIN_FRACTION, 0 = library default
+		LinkPeakGBps: flags.fabricProbeLinkPeak,    // FABRIC_PROBE_LINK_PEAK_GBPS, 0 = calibrated reference
+		TimeoutMs:    5000,
+		Flags:        fabricprobe.FlagFabricHandles | fabricprobe.FlagMigAware,
+	}
+	probe, err := fabricprobe.Open(cfg)
 	switch {
 	case errors.Is(err, fabricprobe.ErrUnsupported):
-		// No libcdprobe.so / no CUDA driver / not sm_100: there is no CPU stand-in. No verdict is
+		// No libcdprobe.so / no CUDA driver / not sm_100: there is no CPU stand-in.  No verdict is
 		// written and check() does not gate on a missing verdict.
 		klog.Infof("fabric probe not supported on this node: %v", err)
-		return stop
+		return p
 	case err != nil:
+		// A node whose probe cannot even be set up is not Ready: leave a failing verdict, not none.
 		klog.Errorf("error opening fabric probe: %v", err)
-		return stop
+		writeVerdict(fabricprobe.Result{}, fmt.Errorf("cdprobe_open: %w", err), flags)
+		return p
 	}
+
 	runOnce := func() {
-		t0 := time.Now()
-		res, err := probe.Run(ctx)
-		klog.V(6).Infof("t_fabric_probe %.6f s", time.Since(t0).Seconds())
-		v := fabricProbeVerdict{TimeUnix: time.Now().Unix(), OK: err == nil && res.Verdict, N: res.N,
-			ProbeMs: res.ProbeMs, ReachRead: res.ReachRead, ReachWrite: res.ReachWrite,
-			GBpsRead: res.GBpsRead, GBpsWrite: res.GBpsWrite}
-		if err != nil {
-			v.Error = err.Error()
-		}
-		for i := 0; i < res.N; i++ {
-			for j := 0; j < res.N; j++ {
-				if i != j && !(res.ReachRead[i*res.N+j] && res.ReachWrite[i*res.N+j]) {
-					v.UnreachablePairs++
-				}
+		if probe == nil { // the previous pass left the handle unusable
+			if probe, err = fabricprobe.Open(cfg); err != nil {
+				klog.Errorf("error reopening fabric probe: %v", err)
+				writeVerdict(fabricprobe.Result{}, fmt.Errorf("cdprobe_open: %w", err), flags)
+				probe = nil
+				return
 			}
 		}
-		if err := writeFileAtomic(fabricProbeVerdictPath, v); err != nil {
-			klog.Errorf("cannot write %s: %v", fabricProbeVerdictPath, err)
+		t0 := time.Now()
+		res, err := probe.Run(ctx)
+		d := time.Since(t0)
+		klog.V(6).Infof("t_fabric_probe %.6f s", d.Seconds())
+		v := writeVerdict(res, err, flags)
+		metrics.ObserveFabricProbe(flags.nodeName, d, v.OK, v.UnreachablePairs, v.SlowPairs, res.N, res.GBpsRead, res.GBpsWrite)
+		klog.Infof("fabric probe: verdict ok=%t, %d GPU(s), %d unreachable pair(s), %d slow pair(s), min read %.0f GB/s, min write %.0f GB/s, %.3f ms",
+			v.OK, v.N, v.UnreachablePairs, v.SlowPairs, v.MinGBpsRead, v.MinGBpsWrite, v.ProbeMs)
+		if err != nil && (errors.Is(err, fabricprobe.ErrTimeout) || errors.Is(err, fabricprobe.ErrState) || errors.Is(err, fabricprobe.ErrCUDA)) {
+			// a timed-out pass may leave the handle sticky (Run then only returns ErrState): start afresh
+			probe.Close()
+			probe = nil
 		}
-		klog.Infof("fabric probe: verdict ok=%t, %d GPU(s), %d unreachable pair(s), %.3f ms", v.OK, v.N,
-			v.UnreachablePairs, v.ProbeMs)
 	}
-	done := make(chan struct{})
+
+	p.kick = make(chan struct{}, 1)
+	p.done = make(chan struct{})
 	go func() {
-		defer close(done)
+		defer close(p.done)
+		defer func() {
+			if probe != nil {
+				probe.Close()
+			}
+		}()
+		var tick <-chan time.Time
+		if flags.fabricProbeInterval > 0 {
+			t := time.NewTicker(flags.fabricProbeInterval)
+			defer t.Stop()
+			tick = t.C
+		}
 		runOnce()
 		for {
 			select {
 			case <-ctx.Done():
 				return
-			case _, ok := <-updates:
-				if !ok {
-					return
-				}
+			case <-p.kick:
+				runOnce()
+			case <-tick:
 				runOnce()
 			}
 		}
 	}()
-	return func() {
-		<-done
-		probe.Close()
+	return p
+}
+
+func writeVerdict(res fabricprobe.Result, runErr error, flags *Flags) fabricProbeVerdict {
+	v := fabricProbeVerdict{
+		Schema: fabricProbeVerdictSchema, TimeUnix: time.Now().Unix(), PodUID: flags.podUID, BootID: bootID(),
+		OK: runErr == nil && res.Verdict, N: res.N,
+		UnreachablePairs: res.UnreachablePairs, SlowPairs: res.SlowPairs,
+		MinGBpsRead: res.MinGBpsRead, MinGBpsWrite: res.MinGBpsWrite,
+		GateGBpsRead: res.GateGBpsRead, GateGBpsWrite: res.GateGBpsWrite,
+		ProbeMs: res.ProbeMs, BytesPerPair: res.BytesPerPair,
+		ReachRead: boolsToInts(res.ReachRead), ReachWrite: boolsToInts(res.ReachWrite),
+		GBpsRead: res.GBpsRead, GBpsWrite: res.GBpsWrite,
 	}
+	if runErr != nil {
+		v.Error = runErr.Error()
+	}
+	if err := writeFileAtomic(fabricProbeVerdictPath, v); err != nil {
+		klog.Errorf("cannot write %s: %v", fabricProbeVerdictPath, err)
+	}
+	return v
 }
 
 // checkFabricProbeVerdict is the addition to check(): a failed verdict makes the pod NotReady; a missing
-// one does not (same spirit as the reference's no-op when CLIQUE_ID is empty, main.go:436-439).
-func checkFabricProbeVerdict() error {
+// one — or one this pod did not write — does not (same spirit as the reference's no-op when CLIQUE_ID is
+// empty, main.go:436-439).
+func checkFabricProbeVerdict(flags *Flags) error {
 	if !featuregates.Enabled(featuregates.FabricProbe) {
 		return nil
 	}
@@ -133,9 +238,26 @@ func checkFabricProbeVerdict() error {
 	if err := json.Unmarshal(raw, &v); err != nil {
 		return fmt.Errorf("fabric probe verdict unreadable: %w", err)
 	}
+	if v.PodUID != "" && flags.podUID != "" && v.PodUID != flags.podUID {
+		return nil // another pod's verdict (the mount outlives pods)
+	}
+	if b := bootID(); v.BootID != "" && b != "" && v.BootID != b {
+		return nil
+	}
+	maxAge := flags.fabricProbeMaxAge // FABRIC_PROBE_MAX_AGE_S
+	if maxAge <= 0 && flags.fabricProbeInterval > 0 {
+		maxAge = 3*flags.fabricProbeInterval + time.Minute // periodic re-probe on: a verdict must keep coming
+	}
+	if age := time.Since(time.Unix(v.TimeUnix, 0)); maxAge > 0 && age > maxAge {
+		return fmt.Errorf("fabric probe verdict is stale (%d s old)", int(age.Seconds()))
+	}
 	if !v.OK {
-		return fmt.Errorf("fabric probe failed: %d unreachable pair(s), min read %.0f GB/s, min write %.0f GB/s: %s",
-			v.UnreachablePairs, v.MinGBpsRead, v.MinGBpsWrite, v.Error)
+		msg := fmt.Sprintf("fabric probe failed: %d unreachable pair(s), %d slow pair(s), min read %.0f GB/s, min write %.0f GB/s",
+			v.UnreachablePairs, v.SlowPairs, v.MinGBpsRead, v.MinGBpsWrite)
+		if v.Error != "" {
+			msg += ": " + v.Error
+		}
+		return errors.New(msg)
 	}
 	return nil
 }

@@ -77,6 +77,14 @@ const (
 // driver, no sm_100 GPU).  There is no CPU fallback: callers decide whether that gates Ready.
 var ErrUnsupported = errors.New("fabricprobe: not supported on this node")
 
+// Errors a Run can wrap (errors.Is).  After ErrTimeout, ErrState or ErrCUDA the handle may be
+// unusable ("sticky"): Close it and Open a new one before the next pass.
+var (
+	ErrTimeout = errors.New("fabricprobe: probe timed out")        // CDPROBE_ERR_TIMEOUT
+	ErrState   = errors.New("fabricprobe: handle is unusable")     // CDPROBE_ERR_STATE
+	ErrCUDA    = errors.New("fabricprobe: CUDA call failed")       // CDPROBE_ERR_CUDA
+)
+
 type Config struct {
 	LibraryPath string // default "libcdprobe.so"
 	Ordinals    []int  // nil = every visible GPU
@@ -85,7 +93,10 @@ type Config struct {
 	Ops         uint32
 	TimeoutMs   uint32
 	Flags       uint32
-	MinFraction float32 // FABRIC_PROBE_MIN_FRACTION; 0 = library default (0.65 of 900 GB/s/dir)
+	MinFraction float32 // FABRIC_PROBE_MIN_FRACTION; 0 = library default (0.90 of the calibrated reference)
+	// FABRIC_PROBE_LINK_PEAK_GBPS; 0 = calibrated reference (what a healthy B200 port delivers to SM-issued
+	// traffic, include/cdprobe.h), > 0 = absolute: the gate is MinFraction x LinkPeakGBps.
+	LinkPeakGBps float32
 }
 
 type Result struct {
@@ -99,6 +110,11 @@ type Result struct {
 	Verdict     bool
 	Aborted     bool
 	BytesPerPair uint64
+	// Slowest filled off-diagonal pair, the GB/s gate the verdict applied (0: bandwidth not judged), and how
+	// many ordered pairs failed it / were unreachable.
+	MinGBpsRead, MinGBpsWrite   float32
+	GateGBpsRead, GateGBpsWrite float32
+	UnreachablePairs, SlowPairs int
 }
 
 type Probe struct {
@@ -131,6 +147,7 @@ func Open(cfg Config) (*Probe, error) {
 	c.timeout_ms = C.uint32_t(cfg.TimeoutMs)
 	c.flags = C.uint32_t(cfg.Flags)
 	c.min_fraction = C.float(cfg.MinFraction)
+	c.link_peak_gbps = C.float(cfg.LinkPeakGBps)
 	var h *C.cdprobe_t
 	if rc := C.cdp_call_open(&c, &h); rc != 0 {
 		err := fmt.Errorf("cdprobe_open: %s: %s", C.GoString(C.cdp_call_strerror(rc)), C.GoString(C.cdp_call_last()))
@@ -155,7 +172,10 @@ func (p *Probe) Run(ctx context.Context) (Result, error) {
 	rc := C.cdp_call_run(p.h, &r)
 	n := int(r.n)
 	out := Result{N: n, ProbeMs: float64(r.probe_ms), Verdict: r.verdict != 0, Aborted: r.aborted != 0,
-		BytesPerPair: uint64(r.bytes_per_pair)}
+		BytesPerPair: uint64(r.bytes_per_pair),
+		MinGBpsRead: float32(r.min_gbps_read), MinGBpsWrite: float32(r.min_gbps_write),
+		GateGBpsRead: float32(r.gate_gbps_read), GateGBpsWrite: float32(r.gate_gbps_write),
+		UnreachablePairs: int(r.unreachable_pairs), SlowPairs: int(r.slow_pairs)}
 	out.ReachRead = make([]bool, n*n)
 	out.ReachWrite = make([]bool, n*n)
 	out.GBpsRead = make([]float32, n*n)
@@ -172,7 +192,17 @@ func (p *Probe) Run(ctx context.Context) (Result, error) {
 		}
 	}
 	if rc != 0 {
-		return out, fmt.Errorf("cdprobe_run: %s: %s", C.GoString(C.cdp_call_strerror(rc)), C.GoString(C.cdp_call_last()))
+		// cdprobe_run zeroes and fills the result before anything can fail, so `out` is well-formed here
+		err := fmt.Errorf("cdprobe_run: %s: %s", C.GoString(C.cdp_call_strerror(rc)), C.GoString(C.cdp_call_last()))
+		switch rc {
+		case C.CDPROBE_ERR_TIMEOUT:
+			err = fmt.Errorf("%w: %v", ErrTimeout, err)
+		case C.CDPROBE_ERR_STATE:
+			err = fmt.Errorf("%w: %v", ErrState, err)
+		case C.CDPROBE_ERR_CUDA:
+			err = fmt.Errorf("%w: %v", ErrCUDA, err)
+		}
+		return out, err
 	}
 	return out, nil
 }

@@ -9,7 +9,18 @@ import (
 	"errors"
 )
 
-var ErrUnsupported = errors.New("fabricprobe: not supported on this node")
+var (
+	ErrUnsupported = errors.New("fabricprobe: not supported on this node")
+	ErrTimeout     = errors.New("fabricprobe: probe timed out")
+	ErrState       = errors.New("fabricprobe: handle is unusable")
+	ErrCUDA        = errors.New("fabricprobe: CUDA call failed")
+)
+
+const (
+	ModeReachOnly, ModeSliced, ModeFull             = 0, 1, 2
+	OpRead, OpWrite                                 = 1, 2
+	FlagFabricHandles, FlagMigAware, FlagLocalDiag = 0x01, 0x02, 0x04
+)
 
 type Config struct {
 	LibraryPath string
@@ -19,7 +30,8 @@ type Config struct {
 	Ops         uint32
 	TimeoutMs   uint32
 	Flags       uint32
-	MinFraction float32
+	MinFraction  float32
+	LinkPeakGBps float32
 }
 
 type Result struct {
@@ -30,6 +42,9 @@ type Result struct {
 	ProbeMs               float64
 	Verdict, Aborted      bool
 	BytesPerPair          uint64
+	MinGBpsRead, MinGBpsWrite   float32
+	GateGBpsRead, GateGBpsWrite float32
+	UnreachablePairs, SlowPairs int
 }
 
 type Probe struct{}

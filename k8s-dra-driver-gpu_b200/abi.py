@@ -6,7 +6,7 @@ import os
 
 MAX_GPUS = 16
 MAX_PHASES = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK = 0
 ERR_ABI, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_TIMEOUT = -1, -2, -3, -4, -5
@@ -24,10 +24,12 @@ FLAG_ALLOW_SAME_DEVICE = 0x40
 FLAG_UNIDIRECTIONAL = 0x80
 FLAG_SERIAL_VERIFY = 0x100
 FLAG_SIMULATE_MIG = 0x200
+FLAG_ALL_RANK_BARRIERS = 0x400
 
 OPT_EVENT_TIMING, OPT_CTAS, OPT_PATH, OPT_TIMEOUT_MS, OPT_OVERLAP_VERIFY, OPT_VERIFY_CTAS = 1, 2, 3, 4, 5, 6
 OPT_UNIDIRECTIONAL = 7
 OPT_WARMUP, OPT_WARMUP_BYTES, OPT_DEBUG_SKIP_RANK = 8, 9, 10
+OPT_CTAS_RANK, OPT_MIN_FRACTION_PPM, OPT_LINK_PEAK_MBPS, OPT_SOLO_RANK, OPT_ALL_RANK_BARRIERS = 11, 12, 13, 14, 15
 
 _N2 = MAX_GPUS * MAX_GPUS
 
@@ -82,6 +84,10 @@ class ResultT(C.Structure):
         ("event_ms", C.c_double * MAX_GPUS),
         ("min_gbps_read", C.c_float),
         ("min_gbps_write", C.c_float),
+        ("gate_gbps_read", C.c_float),
+        ("gate_gbps_write", C.c_float),
+        ("unreachable_pairs", C.c_uint32),
+        ("slow_pairs", C.c_uint32),
     ]
 
 
@@ -133,6 +139,7 @@ class TraceT(C.Structure):
         ("peer0", C.c_int8 * MAX_PHASES),
         ("peer1", C.c_int8 * MAX_PHASES),
         ("sync_all", C.c_uint8 * MAX_PHASES),
+        ("sync_mask", C.c_uint16 * MAX_PHASES),
         ("t_start", C.c_uint64 * MAX_PHASES),
         ("t_end0", C.c_uint64 * MAX_PHASES),
         ("t_end1", C.c_uint64 * MAX_PHASES),
@@ -167,6 +174,7 @@ class ScheduleT(C.Structure):
         ("cta0", (C.c_uint16 * MAX_PHASES) * 2),
         ("nctas", (C.c_uint16 * MAX_PHASES) * 2),
         ("sync_all", C.c_uint8 * MAX_PHASES),
+        ("sync_mask", C.c_uint16 * MAX_PHASES),
     ]
 
 
@@ -184,6 +192,8 @@ SYMBOLS = {
     "cdprobe_remap_peer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cdprobe_unmap_peer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cdprobe_corrupt": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]),
+    "cdprobe_ce_copy": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32,
+                                  C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]),
     "cdprobe_close": (None, [C.c_void_p]),
     "cdprobe_plan": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(PlanT)]),
     "cdprobe_topology": (C.c_int, [C.c_uint32, C.POINTER(TopologyT)]),

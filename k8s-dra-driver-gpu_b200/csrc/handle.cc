@@ -98,6 +98,8 @@ struct cdprobe {
   double last_run_end_ms = -1.0;
   bool warm_now = false;
   uint32_t debug_skip_rank = 0;  // 1-based local rank whose kernel is NOT launched (fault injection)
+  uint32_t solo_rank = 0;        // 1-based local rank that runs alone, no cross-GPU barrier (ncu captures)
+  double last_probe_ms = 0.0;    // host wall clock of the previous run (wait_rows: how long to spin hot)
   uint32_t verify_ctas = 32;  // CTAs that verify landing slots under CDPROBE_FLAG_OVERLAP_VERIFY
   double open_ms = 0, fill_ms = 0;
 };
@@ -243,8 +245,18 @@ static void fill_params(const cdprobe* h, uint32_t li, const Phase* phases, uint
 }
 
 // Waits until every local row carries `token`; returns false on host timeout or a kernel error.
+// The rows are pinned host words the kernels write themselves.  A healthy probe is over in 0.5-3.3 ms,
+// so the wait spins hot for as long as a healthy run can plausibly take (twice the previous run, at
+// least 2 ms, at most 50 ms) and then backs off to a 100 us sleep between polls: a hung peer costs the
+// daemon pod a sleeping thread for timeout_ms, not a core burnt inside its CPU limit.
 static bool wait_rows(cdprobe* h, uint64_t token) {
-  const double t_end = now_ms() + h->cfg.timeout_ms + 2000.0;
+  const double t_begin = now_ms();
+  const double t_end = t_begin + h->cfg.timeout_ms + 2000.0;
+  double hot_ms = 2.0 * h->last_probe_ms;
+  if (hot_ms < 2.0) hot_ms = 2.0;
+  if (hot_ms > 50.0) hot_ms = 50.0;
+  const double t_hot = t_begin + hot_ms;
+  bool hot = true;
   uint32_t spins = 0;
   for (;;) {
     bool all = true;
@@ -258,15 +270,24 @@ static bool wait_rows(cdprobe* h, uint64_t token) {
       __sync_synchronize();
       return true;
     }
-    if ((++spins & 0x3ffu) == 0) {
-      if (now_ms() > t_end) return false;
-      // surface asynchronous launch/kernel errors instead of spinning on them
-      for (uint32_t li = 0; li < h->n_local; ++li) {
-        cudaSetDevice(h->lr[li].ordinal);
-        cudaError_t q = cudaStreamQuery(h->lr[li].stream);
-        if (q != cudaSuccess && q != cudaErrorNotReady) {
-          set_err(std::string("kernel failed: ") + cudaGetErrorName(q));
-          return false;
+    if (!hot) {
+      timespec ts = {0, 100000};
+      nanosleep(&ts, nullptr);
+    }
+    if (!hot || (++spins & 0x3ffu) == 0) {
+      const double t = now_ms();
+      if (t > t_end) return false;
+      if (hot && t > t_hot) hot = false;
+      if (hot || (++spins & 0x3fu) == 0) {
+        // surface asynchronous launch/kernel errors instead of waiting on them
+        for (uint32_t li = 0; li < h->n_local; ++li) {
+          if (h->solo_rank && h->solo_rank != li + 1) continue;
+          cudaSetDevice(h->lr[li].ordinal);
+          cudaError_t q = cudaStreamQuery(h->lr[li].stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) {
+            set_err(std::string("kernel failed: ") + cudaGetErrorName(q));
+            return false;
+          }
         }
       }
     }
@@ -314,7 +335,7 @@ static int fill_and_publish(cdprobe* h) {
       ph[s].job[0].slot = (uint8_t)s;
       ph[s].job[0].cta0 = 0;
       ph[s].job[0].nctas = (uint16_t)L.ctas;
-      ph[s].sync_all = 0;
+      ph[s].sync_mask = 0;
     }
     ProbeParams P;
     fill_params(h, li, ph, pl.n_slices, 0u, &P);
@@ -384,8 +405,8 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
   if (c.ops == 0) c.ops = CDPROBE_OP_READ | CDPROBE_OP_WRITE;
   if (c.ops & ~(CDPROBE_OP_READ | CDPROBE_OP_WRITE)) return CDPROBE_ERR_ARG;
   if (c.timeout_ms == 0) c.timeout_ms = 5000;
-  if (c.min_fraction <= 0.f) c.min_fraction = 0.65f;  // see include/cdprobe.h: measured healthy floor on B200
-  if (c.link_peak_gbps <= 0.f) c.link_peak_gbps = 900.f;
+  // gate: see gate_gbps(); 0 in either field selects the default at verdict time
+  if (c.link_peak_gbps < 0.f || c.min_fraction < 0.f) return CDPROBE_ERR_ARG;
   if (c.world_size == 0) c.world_size = 1;
   if (c.rank >= c.world_size) return CDPROBE_ERR_ARG;
   h->path = (c.flags & CDPROBE_FLAG_PATH_LDST) ? 1u : 0u;
@@ -615,10 +636,35 @@ static int open_impl(const cdprobe_config_t* cfg, cdprobe* h) {
   return CDPROBE_OK;
 }
 
+// The GB/s an ordered pair must reach for a passing verdict (0: bandwidth is not judged).
+//   link_peak_gbps > 0 : absolute, min_fraction x link_peak_gbps (default fraction 0.65: the round-1 gate
+//                        against nominal 900).
+//   link_peak_gbps == 0: calibrated.  What a healthy B200 port delivers to SM-issued traffic, measured on
+//                        the same box next to the copy engine (tools/linkbench.cu ->
+//                        profiles/r02_linkbench_n2.jsonl), de-rated for the ~8 us a phase spends ramping and
+//                        draining; default fraction 0.90.  Run-to-run spread of a pair is 0.2-0.7 %, spread
+//                        across pairs and boxes ~3 %: 0.90 leaves healthy hardware a 7 % margin, while a
+//                        port that lost 2 of its 18 links (-11 %) fails.
+struct HealthyRates {  // GB/s per direction per GPU, 1 GiB transfers
+  double read_bidi = 672.0, write_bidi = 703.0, read_uni = 785.0, write_uni = 714.7;
+  double phase_overhead_ns = 8000.0;
+};
+static float gate_gbps(const cdprobe* h, bool is_read) {
+  if (h->cfg.mode == CDPROBE_MODE_REACH_ONLY || h->n_total <= 1) return 0.f;
+  if (h->cfg.link_peak_gbps > 0.f) return (h->cfg.min_fraction > 0.f ? h->cfg.min_fraction : 0.65f) * h->cfg.link_peak_gbps;
+  const HealthyRates hr;
+  const bool uni = (h->cfg.flags & CDPROBE_FLAG_UNIDIRECTIONAL) != 0;
+  const double rate = is_read ? (uni ? hr.read_uni : hr.read_bidi) : (uni ? hr.write_uni : hr.write_bidi);
+  const double bpp = (double)h->plan.bpp;
+  const double expected = bpp / (bpp / rate + hr.phase_overhead_ns);  // bytes per ns == GB/s
+  return (float)((h->cfg.min_fraction > 0.f ? h->cfg.min_fraction : 0.90f) * expected);
+}
+
 static void assemble(const cdprobe* h, cdprobe_result_t* out) {
   const Plan& pl = h->plan;
-  const double peak = h->cfg.link_peak_gbps, minf = h->cfg.min_fraction;
-  const bool judge_bw = h->cfg.mode != CDPROBE_MODE_REACH_ONLY;
+  const float gate_r = gate_gbps(h, true), gate_w = gate_gbps(h, false);
+  out->gate_gbps_read = gate_r;
+  out->gate_gbps_write = gate_w;
   bool verdict = true;
   float min_r = 0.f, min_w = 0.f;
   bool have_r = false, have_w = false;
@@ -635,6 +681,7 @@ static void assemble(const cdprobe* h, cdprobe_result_t* out) {
     if (row->aborted) out->aborted = 1;
     out->device_ms[li] = row->t_last > row->t_first ? (double)(row->t_last - row->t_first) / 1e6 : 0.0;
     double bar_ns = 0.0;
+    bool slow[kMaxRanks] = {};
     for (uint32_t p = 0; p < L.n_phases; ++p) {
       const PhaseOut& o = row->ph[p];
       if (p + 1 < L.n_phases) {
@@ -656,7 +703,7 @@ static void assemble(const cdprobe* h, cdprobe_result_t* out) {
         if (offdiag) {
           if (!have_r || gbps < min_r) min_r = gbps;
           have_r = true;
-          if (!ok || (judge_bw && h->n_total > 1 && gbps < minf * peak)) verdict = false;
+          if (ok && (uint32_t)job.peer != g && gbps < gate_r) slow[job.peer] = true;
         }
       } else {
         const bool ok = done && o.verdict[0] == h->launch_seq * 4ull + kVerdictOk;
@@ -667,20 +714,28 @@ static void assemble(const cdprobe* h, cdprobe_result_t* out) {
         if (offdiag) {
           if (!have_w || gbps < min_w) min_w = gbps;
           have_w = true;
-          if (!ok || (judge_bw && h->n_total > 1 && gbps < minf * peak)) verdict = false;
+          if (ok && (uint32_t)job.peer != g && gbps < gate_w) slow[job.peer] = true;
         }
       }
     }
     out->barrier_us[li] = bar_ns / 1e3;
-    // every off-diagonal cell of this row must have been probed and reachable
+    // every off-diagonal cell of this row must have been probed, reachable and at speed
     for (uint32_t j = 0; j < h->n_total; ++j) {
       if (j == g) continue;
       // P2P is not applicable between MIG instances: the cell stays 0 but must not turn a MIG-only
       // domain NotReady
       if (h->status[g][j] == CDPROBE_ERR_UNSUPPORTED || h->status[j][g] == CDPROBE_ERR_UNSUPPORTED) continue;
       const uint32_t idx = g * CDPROBE_MAX_GPUS + j;
-      if ((h->cfg.ops & CDPROBE_OP_READ) && !out->reach_read[idx]) verdict = false;
-      if ((h->cfg.ops & CDPROBE_OP_WRITE) && !out->reach_write[idx]) verdict = false;
+      const bool unreachable = ((h->cfg.ops & CDPROBE_OP_READ) && !out->reach_read[idx]) ||
+                               ((h->cfg.ops & CDPROBE_OP_WRITE) && !out->reach_write[idx]);
+      if (unreachable) out->unreachable_pairs++;
+      else if (slow[j]) out->slow_pairs++;
+      if (unreachable || slow[j]) verdict = false;
+    }
+    if (h->n_total == 1 && pl.diag) {  // loop-back: reachability only (HBM speed is not a fabric property)
+      const uint32_t idx = g * CDPROBE_MAX_GPUS + g;
+      if (((h->cfg.ops & CDPROBE_OP_READ) && !out->reach_read[idx]) || ((h->cfg.ops & CDPROBE_OP_WRITE) && !out->reach_write[idx]))
+        verdict = false;
     }
   }
   out->min_gbps_read = min_r;
@@ -735,13 +790,18 @@ int cdprobe_open(const cdprobe_config_t* cfg, cdprobe_t** out) {
 int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
   cdp::g_last_error.clear();
   if (h == nullptr || out == nullptr) return CDPROBE_ERR_ARG;
-  if (h->sticky) return CDPROBE_ERR_STATE;
-  const double t0 = cdp::now_ms();
+  // The caller reads *out whatever the return code (the daemon writes a verdict from it): never leave it
+  // as it came in.
   memset(out, 0, sizeof(*out));
   out->abi = CDPROBE_ABI_VERSION;
   out->n = h->n_total;
   out->bytes_per_pair = h->plan.bpp;
   out->rounds = h->plan.rounds;
+  if (h->sticky) {
+    cdp::set_err("handle is unusable after an earlier timeout or CUDA error: close it and open a new one");
+    return CDPROBE_ERR_STATE;
+  }
+  const double t0 = cdp::now_ms();
   h->launch_seq++;
   out->run_seq = h->launch_seq;
   h->warm_now = h->warm_mode == 2 ||
@@ -749,15 +809,28 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
   cdp::ProbeParams P;
   for (uint32_t li = 0; li < h->n_local; ++li) {
     cdp::LocalRank& L = h->lr[li];
-    if (h->debug_skip_rank == li + 1) {  // fault injection: this rank never shows up at the barriers
+    const bool skipped = h->debug_skip_rank == li + 1 || (h->solo_rank != 0 && h->solo_rank != li + 1);
+    if (skipped) {  // fault injection / solo profiling: this rank never shows up at the barriers
       memset(L.row->ph, 0, sizeof(L.row->ph));
-      L.row->aborted = 1;
+      L.row->aborted = h->solo_rank ? 0u : 1u;
       L.row->n_phases = L.n_phases;
       L.row->t_first = L.row->t_last = 0;
       L.row->done = h->launch_seq;
       continue;
     }
-    cdp::fill_params(h, li, L.phases, L.n_phases, L.peer_mask, &P);
+    if (h->solo_rank == li + 1) {
+      // only this rank's own transfers; nobody to wait for, nobody verifies (reach_write stays 0)
+      cdp::Phase solo[cdp::kMaxPhases];
+      for (uint32_t p = 0; p < L.n_phases; ++p) {
+        solo[p] = L.phases[p];
+        solo[p].sync_mask = 0;
+        for (int jb = 0; jb < 2; ++jb)
+          if (solo[p].job[jb].kind == cdp::kJobVerify) solo[p].job[jb].kind = cdp::kJobNone;
+      }
+      cdp::fill_params(h, li, solo, L.n_phases, 0u, &P);
+    } else {
+      cdp::fill_params(h, li, L.phases, L.n_phases, L.peer_mask, &P);
+    }
     if (h->event_timing) {
       cudaSetDevice(L.ordinal);
       cudaEventRecord(L.ev0, L.stream);
@@ -780,10 +853,12 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
   cdp::assemble(h, out);
   h->last_run_end_ms = cdp::now_ms();
   out->probe_ms = h->last_run_end_ms - t0;
+  h->last_probe_ms = out->probe_ms;
   out->warmed = (h->warm_now && h->plan.rounds > 0) ? 1u : 0u;  // N = 1 has no link to wake
   if (h->event_timing) {  // after probe_ms: the event round trip is not part of the probe
     for (uint32_t li = 0; li < h->n_local; ++li) {
       cdp::LocalRank& L = h->lr[li];
+      if (h->debug_skip_rank == li + 1 || (h->solo_rank != 0 && h->solo_rank != li + 1)) continue;
       float ms = 0.f;
       cudaSetDevice(L.ordinal);
       if (cudaEventSynchronize(L.ev1) == cudaSuccess && cudaEventElapsedTime(&ms, L.ev0, L.ev1) == cudaSuccess)
@@ -835,6 +910,8 @@ int cdprobe_gather(cdprobe_t* h, cdprobe_result_t* inout) {
     }
     if (!o.verdict) inout->verdict = 0;
     if (o.aborted) inout->aborted = 1;
+    inout->unreachable_pairs += o.unreachable_pairs;
+    inout->slow_pairs += o.slow_pairs;
     if (o.min_gbps_read > 0.f && (inout->min_gbps_read == 0.f || o.min_gbps_read < inout->min_gbps_read))
       inout->min_gbps_read = o.min_gbps_read;
     if (o.min_gbps_write > 0.f && (inout->min_gbps_write == 0.f || o.min_gbps_write < inout->min_gbps_write))
@@ -889,7 +966,8 @@ int cdprobe_trace(cdprobe_t* h, uint32_t local, cdprobe_trace_t* out) {
     out->kind1[p] = L.phases[p].job[1].kind;
     out->peer0[p] = L.phases[p].job[0].peer;
     out->peer1[p] = L.phases[p].job[1].peer;
-    out->sync_all[p] = (uint8_t)L.phases[p].sync_all;
+    out->sync_mask[p] = (uint16_t)(L.phases[p].sync_mask & L.peer_mask);
+    out->sync_all[p] = (uint8_t)(L.peer_mask != 0 && (L.phases[p].sync_mask & L.peer_mask) == L.peer_mask);
     out->t_start[p] = rel(o.t_start);
     out->t_end0[p] = rel(o.t_end[0]);
     out->t_end1[p] = rel(o.t_end[1]);
@@ -942,6 +1020,37 @@ int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
       }
       return rc;
     }
+    case CDPROBE_OPT_ALL_RANK_BARRIERS:
+    {
+      const uint32_t old = h->cfg.flags;
+      h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_ALL_RANK_BARRIERS) | (value ? CDPROBE_FLAG_ALL_RANK_BARRIERS : 0u);
+      const int rc = cdp::rebuild_all(h);
+      if (rc != CDPROBE_OK) {
+        h->cfg.flags = old;
+        cdp::rebuild_all(h);
+      }
+      return rc;
+    }
+    case CDPROBE_OPT_CTAS_RANK:
+    {
+      const uint32_t li = (uint32_t)(value >> 16), c = (uint32_t)(value & 0xffffu);
+      if (li == 0 || li > h->n_local || c == 0) return CDPROBE_ERR_ARG;
+      cdp::LocalRank& L = h->lr[li - 1];
+      L.ctas = c > (uint32_t)L.max_ctas ? (uint32_t)L.max_ctas : c;
+      return cdp::rebuild_all(h);
+    }
+    case CDPROBE_OPT_MIN_FRACTION_PPM:
+      if (value > 100000000ull) return CDPROBE_ERR_ARG;
+      h->cfg.min_fraction = (float)((double)value / 1e6);
+      return CDPROBE_OK;
+    case CDPROBE_OPT_LINK_PEAK_MBPS:
+      if (value > 100000000000ull) return CDPROBE_ERR_ARG;
+      h->cfg.link_peak_gbps = (float)((double)value / 1e3);
+      return CDPROBE_OK;
+    case CDPROBE_OPT_SOLO_RANK:
+      if (value > h->n_local || h->cfg.world_size > 1) return CDPROBE_ERR_ARG;
+      h->solo_rank = (uint32_t)value;
+      return CDPROBE_OK;
     case CDPROBE_OPT_DEBUG_SKIP_RANK:
       if (value > h->n_local) return CDPROBE_ERR_ARG;
       h->debug_skip_rank = (uint32_t)value;
@@ -974,14 +1083,22 @@ int cdprobe_unmap_peer(cdprobe_t* h, uint32_t local, uint32_t peer) {
 
 int cdprobe_remap_peer(cdprobe_t* h, uint32_t local, uint32_t peer) {
   if (h == nullptr || local >= h->n_local || peer >= h->n_total) return CDPROBE_ERR_ARG;
-  if (h->cfg.world_size > 1) return CDPROBE_ERR_UNSUPPORTED;
   const uint32_t g = h->lr[local].grank;
   if (peer == g) return CDPROBE_ERR_ARG;
+  if (h->sticky) return CDPROBE_ERR_STATE;
   cdp::unmap_peer(h, local, peer);
-  h->status[g][peer] = cdp::map_peer(h, local, peer);
+  const int32_t st = cdp::map_peer(h, local, peer);
+  if (st != 0 && h->cfg.world_size > 1) {
+    // the other processes build their phase tables from the mapping status exchanged at open and would
+    // not learn that this pair is gone: the domain has to be reopened
+    h->sticky = true;
+    cdp::set_err("re-mapping a peer failed in a multi-process domain: " + h->drv.error_name((CUresult)st));
+    return CDPROBE_ERR_CUDA;
+  }
+  h->status[g][peer] = st;
   const int rc = cdp::rebuild_all(h);
   if (rc != CDPROBE_OK) return rc;
-  return h->status[g][peer] == 0 ? CDPROBE_OK : CDPROBE_ERR_CUDA;
+  return st == 0 ? CDPROBE_OK : CDPROBE_ERR_CUDA;
 }
 
 int cdprobe_corrupt(cdprobe_t* h, uint32_t local, uint64_t byte_offset, uint64_t xor_mask) {
@@ -996,6 +1113,49 @@ int cdprobe_corrupt(cdprobe_t* h, uint32_t local, uint64_t byte_offset, uint64_t
   w ^= xor_mask;
   CDP_RT(cudaMemcpyAsync(p, &w, 8, cudaMemcpyHostToDevice, L.stream));
   CDP_RT(cudaStreamSynchronize(L.stream));
+  return CDPROBE_OK;
+}
+
+int cdprobe_ce_copy(cdprobe_t* h, uint32_t n_copies, const uint32_t* local, const uint32_t* peer, uint32_t push,
+                    uint64_t bytes, uint32_t reps, double* ms_out) {
+  cdp::g_last_error.clear();
+  if (h == nullptr || local == nullptr || peer == nullptr || ms_out == nullptr || n_copies == 0 ||
+      n_copies > h->n_local || reps == 0 || reps > 1024)
+    return CDPROBE_ERR_ARG;
+  if (h->sticky) return CDPROBE_ERR_STATE;
+  const cdp::Plan& pl = h->plan;
+  uint64_t nb = bytes;
+  if (nb == 0 || nb > pl.src_bytes) nb = pl.src_bytes;
+  if (nb > pl.land_bytes) nb = pl.land_bytes;
+  for (uint32_t k = 0; k < n_copies; ++k) {
+    if (local[k] >= h->n_local || peer[k] >= h->n_total) return CDPROBE_ERR_ARG;
+    for (uint32_t q = 0; q < k; ++q)
+      if (local[q] == local[k]) return CDPROBE_ERR_ARG;  // one copy per local rank: each has one stream and event pair
+    const cdp::LocalRank& L = h->lr[local[k]];
+    if (!L.mapped[peer[k]]) {
+      cdp::set_err("peer is not mapped into this rank's address space");
+      return CDPROBE_ERR_STATE;
+    }
+  }
+  for (uint32_t k = 0; k < n_copies; ++k) {
+    cdp::LocalRank& L = h->lr[local[k]];
+    CDP_RT(cudaSetDevice(L.ordinal));
+    const uint8_t* mine = reinterpret_cast<const uint8_t*>(L.va[L.grank]);
+    const uint8_t* theirs = reinterpret_cast<const uint8_t*>(L.va[peer[k]]);
+    const void* src = push ? mine + pl.src_off : theirs + pl.src_off;
+    void* dst = const_cast<uint8_t*>(push ? theirs : mine) + pl.land_off;
+    CDP_RT(cudaEventRecord(L.ev0, L.stream));
+    for (uint32_t r = 0; r < reps; ++r) CDP_RT(cudaMemcpyAsync(dst, src, nb, cudaMemcpyDeviceToDevice, L.stream));
+    CDP_RT(cudaEventRecord(L.ev1, L.stream));
+  }
+  for (uint32_t k = 0; k < n_copies; ++k) {
+    cdp::LocalRank& L = h->lr[local[k]];
+    CDP_RT(cudaSetDevice(L.ordinal));
+    CDP_RT(cudaEventSynchronize(L.ev1));
+    float ms = 0.f;
+    CDP_RT(cudaEventElapsedTime(&ms, L.ev0, L.ev1));
+    ms_out[k] = ms;
+  }
   return CDPROBE_OK;
 }
 

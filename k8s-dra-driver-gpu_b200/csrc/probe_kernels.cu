@@ -173,12 +173,38 @@ __device__ __noinline__ bool check_abort(const Ctx& c) {
   return false;
 }
 
-__device__ __forceinline__ void mbar_wait(Ctx& c, int stage) {
+// Waits for the bulk load armed on `stage`.  Returns false when the run was aborted while waiting —
+// the load is then STILL IN FLIGHT towards this CTA's shared memory and the caller must drain it
+// (mbar_drain) before the CTA may exit or reuse the stage.
+__device__ __forceinline__ bool mbar_wait(Ctx& c, int stage) {
   const uint32_t bar = c.bar_smem + 8u * stage;
   const uint32_t parity = (c.parity_bits >> stage) & 1u;
   uint32_t spins = 0;
+  bool ok = true;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0u && check_abort(c)) break;
+    if ((++spins & 255u) == 0u && check_abort(c)) {
+      ok = false;
+      break;
+    }
+  }
+  // warp-uniform outcome: a lane that saw the phase complete while another saw the abort must not
+  // flip its parity alone (mbar_drain re-waits the same phase; a completed one passes at once)
+  if (!__all_sync(0xffffffffu, ok)) return false;
+  c.parity_bits ^= (1u << stage);
+  return true;
+}
+// After an abort: wait, without the watchdog, for a load that was already issued.  An abort means a PEER
+// missed a barrier; the memory this load targets is mapped and the copy completes in microseconds.  If
+// it has not after kDrainNs the fabric itself is gone: trap (sticky error on the context, reported by
+// the host as a kernel failure) rather than let a bulk copy land in the shared memory of an exited CTA.
+constexpr uint64_t kDrainNs = 200ull * 1000 * 1000;
+__device__ __noinline__ void mbar_drain(Ctx& c, int stage) {
+  const uint32_t bar = c.bar_smem + 8u * stage;
+  const uint32_t parity = (c.parity_bits >> stage) & 1u;
+  const uint64_t t_give_up = gtimer() + kDrainNs;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0u && gtimer() > t_give_up) __trap();
   }
   c.parity_bits ^= (1u << stage);
 }
@@ -207,17 +233,27 @@ __device__ __forceinline__ void issue_load(const Ctx& c, const uint8_t* base, ui
 __device__ void job_read_tma(Ctx& c, const uint8_t* base, uint64_t bytes, uint32_t gwarp, uint32_t nwarps, Sum& a) {
   const uint64_t n_units = (bytes + kUnitBytes - 1) / kUnitBytes;
   uint64_t u_issue = gwarp;
+  uint32_t in_flight = 0;  // loads issued and not yet waited for (warp-uniform)
   if (c.lane == 0) fence_proxy_async_global();  // data may have been written through the generic proxy
 #pragma unroll
   for (int s = 0; s < kStages; ++s) {
     if (u_issue < n_units) {
       if (c.lane == 0) issue_load(c, base, bytes, u_issue, s);
       u_issue += nwarps;
+      ++in_flight;
     }
   }
   int s = 0;
   for (uint64_t u = gwarp; u < n_units; u += nwarps) {
-    mbar_wait(c, s);
+    if (!mbar_wait(c, s)) {
+      // aborted: stop issuing, but every load already in flight must land before this CTA can exit
+      for (; in_flight > 0; --in_flight) {
+        mbar_drain(c, s);
+        s = (s + 1 == kStages) ? 0 : s + 1;
+      }
+      return;
+    }
+    --in_flight;
     const uint64_t left = bytes - u * kUnitBytes;
     const uint32_t nvec = (left < kUnitBytes ? static_cast<uint32_t>(left) : kUnitBytes) >> 4;
     const uint32_t sbase = c.stage_smem + s * kUnitBytes + c.lane * 16u;
@@ -248,6 +284,7 @@ __device__ void job_read_tma(Ctx& c, const uint8_t* base, uint64_t bytes, uint32
         issue_load(c, base, bytes, u_issue, s);
       }
       u_issue += nwarps;
+      ++in_flight;
     }
     s = (s + 1 == kStages) ? 0 : s + 1;
   }
@@ -432,8 +469,11 @@ __device__ void phase_epilogue(const ProbeParams& P, Ctrl* ctrl, int ph, bool is
   }
 }
 
-// Barrier b: b == 0 opens the run, barrier b >= 1 closes phase b - 1.
-__device__ void barrier(const ProbeParams& P, Ctx& c, int b, bool sync_all) {
+// Barrier b: b == 0 opens the run, barrier b >= 1 closes phase b - 1.  `mask` = the ranks whose
+// traffic touches the same NVLink ports as this rank's in the phases either side of the barrier
+// (schedule.cc: current partner, next partner and their partners; every rank at open and close).
+// The relation is symmetric, so every rank this one waits for also signals it.
+__device__ void barrier(const ProbeParams& P, Ctx& c, int b, uint32_t mask) {
   __syncthreads();
   if (threadIdx.x == 0) {
     Ctrl* ctrl = c.ctrl;
@@ -451,16 +491,16 @@ __device__ void barrier(const ProbeParams& P, Ctx& c, int b, bool sync_all) {
         const uint64_t t_arr = gtimer();
         if (b >= 1) phase_epilogue(P, ctrl, b - 1, false);
         bool timed_out = false;
-        if (sync_all) {
+        if (mask) {
           // One system-scope fence, then relaxed flag stores that pipeline over NVLink.  (A
           // st.release.sys per peer serialises a round trip per store: ~2 us x 7 peers per barrier.)
           __threadfence_system();
           for (uint32_t j = 0; j < P.n_ranks; ++j) {
-            if (j == P.rank || !((P.peer_mask >> j) & 1u)) continue;
+            if (j == P.rank || !((mask >> j) & 1u)) continue;
             st_relaxed_sys(&reinterpret_cast<Ctrl*>(P.base_peer[j])->flags[P.rank].v, target);
           }
           for (uint32_t j = 0; j < P.n_ranks && !timed_out; ++j) {
-            if (j == P.rank || !((P.peer_mask >> j) & 1u)) continue;
+            if (j == P.rank || !((mask >> j) & 1u)) continue;
             uint32_t spins = 0;
             while (ld_acquire_sys(&ctrl->flags[j].v) < target) {
               if ((++spins & 63u) == 0u && check_abort(c)) {
@@ -521,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
   __syncthreads();
   c.deadline = s_deadline;
 
-  barrier(P, c, 0, true);
+  barrier(P, c, 0, P.peer_mask);
 
   for (uint32_t ph = 0; ph < P.n_phases; ++ph) {
     const Phase& phd = P.phase[ph];
@@ -583,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
         atomicMax(&acc->t_end, (unsigned long long)gtimer());
       }
     }
-    barrier(P, c, (int)ph + 1, phd.sync_all != 0u);
+    barrier(P, c, (int)ph + 1, phd.sync_mask & P.peer_mask);
   }
 
   // ---- output: CTA 0 writes the result row into pinned host memory ----------

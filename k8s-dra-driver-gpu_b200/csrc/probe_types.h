@@ -83,7 +83,7 @@ struct Job {            // 16 bytes
 
 struct Phase {          // 40 bytes
   Job job[2];
-  uint32_t sync_all;    // 1: barrier after the phase spans all ranks, 0: this GPU only
+  uint32_t sync_mask;   // ranks this GPU exchanges barrier flags with when the phase closes (0: this GPU only)
   uint32_t pad;
 };
 

@@ -35,15 +35,17 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
   };
   bool overflow = false;
   Phase scratch;
-  auto push = [&](uint8_t kind, int peer, uint32_t slot, uint32_t writer, bool sync_all) -> Phase& {
+  int cur_round = -1;               // tournament round of the phases being pushed (-1: local-only phases)
+  int phase_round[kMaxPhases];      // per phase: the round whose pairing decides which NVLink ports it loads
+  auto push = [&](uint8_t kind, int peer, uint32_t slot, uint32_t writer) -> Phase& {
     if (n >= (uint32_t)kMaxPhases) {
       overflow = true;
       return scratch;
     }
+    phase_round[n] = cur_round;
     Phase& p = phases[n++];
     memset(&p, 0, sizeof(p));
     set_job(p.job[0], kind, peer, slot, writer, 0, ctas);
-    p.sync_all = sync_all ? 1u : 0u;
     return p;
   };
   const uint32_t vctas = in.verify_ctas;
@@ -71,11 +73,13 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
     // streams a small prefix of its round-0 partner's slice, untimed; the phase always exists (all
     // ranks need the same barrier sequence) and each rank decides its own byte count at launch (0 when
     // its previous run ended less than warm_idle_ms ago).
+    cur_round = 0;
     const int p0 = pl.partner[0][g];
     const bool ok0 = p0 >= 0 && pair_ok(g, (uint32_t)p0);
-    push(ok0 ? kJobWarm : kJobNone, ok0 ? p0 : (int)g, ok0 ? slot_of(g, (uint32_t)p0) : 0, 0, true);
+    push(ok0 ? kJobWarm : kJobNone, ok0 ? p0 : (int)g, ok0 ? slot_of(g, (uint32_t)p0) : 0, 0);
   }
   for (uint32_t r = 0; r < pl.rounds; ++r) {
+    cur_round = (int)r;
     const int p = pl.partner[r][g];
     const bool ok = p >= 0 && pair_ok(g, (uint32_t)p);
     const uint32_t slot = ok ? slot_of(g, (uint32_t)p) : 0;
@@ -86,7 +90,7 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
       // write first, then read: the slot the partner fills during the write phase is verified by the
       // spare CTAs during the read phase of the SAME round, so no verify is left over at the end
       if (ops & CDPROBE_OP_WRITE) {
-        Phase& ph = push(mine ? kJobWrite : kJobNone, mine ? p : (int)g, slot, 0, true);
+        Phase& ph = push(mine ? kJobWrite : kJobNone, mine ? p : (int)g, slot, 0);
         if (overlap) {
           attach(ph);
           if (p >= 0 && p_active) {  // what the partner stores into my landing area during this phase
@@ -98,7 +102,7 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
         }
       }
       if (ops & CDPROBE_OP_READ) {
-        Phase& ph = push(mine ? kJobRead : kJobNone, mine ? p : (int)g, slot, 0, true);
+        Phase& ph = push(mine ? kJobRead : kJobNone, mine ? p : (int)g, slot, 0);
         if (overlap) attach(ph);
       }
     }
@@ -106,12 +110,13 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
   // Loop-back (N = 1, or CDPROBE_FLAG_LOCAL_DIAG): same shape as a round — write the diagonal slot,
   // then read the source slice on half the CTAs while the other half verifies what was just written
   // (both jobs are HBM-bound, hence the near-even split).  One barrier fewer than read / write / verify.
+  cur_round = -1;
   const bool diag_overlap = pl.diag && (in.flags & CDPROBE_FLAG_OVERLAP_VERIFY) && (ops & CDPROBE_OP_WRITE) &&
                             (ops & CDPROBE_OP_READ) && ctas >= 2;
   if (pl.diag) {
-    if (ops & CDPROBE_OP_WRITE) push(kJobWrite, (int)g, pl.diag_slot, 0, false);
+    if (ops & CDPROBE_OP_WRITE) push(kJobWrite, (int)g, pl.diag_slot, 0);
     if (ops & CDPROBE_OP_READ) {
-      Phase& ph = push(kJobRead, (int)g, pl.diag_slot, 0, false);
+      Phase& ph = push(kJobRead, (int)g, pl.diag_slot, 0);
       if (diag_overlap) {
         // measured at N = 1 with an even split: the verify half (reading lines that were just written)
         // runs ~5 % slower than the source read, so it gets 33/64 of the CTAs (76 of 148)
@@ -130,9 +135,9 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
       // rank that sat out the last round of an odd-sized domain pushes an idle phase) so that every
       // rank has the same number of barriers.
       if (!(ops & CDPROBE_OP_READ))
-        push(pend.have && pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, false);
+        push(pend.have && pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer);
       pend.have = false;
-      if (pl.diag && !diag_overlap) push(kJobVerify, (int)g, pl.diag_slot, g, false);
+      if (pl.diag && !diag_overlap) push(kJobVerify, (int)g, pl.diag_slot, g);
     } else {
       for (uint32_t s = 0; s < pl.n_slots; ++s) {
         uint32_t writer;
@@ -145,7 +150,7 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
           writer = s < g ? s : s + 1;
           ok = pair_ok(g, writer);
         }
-        push(ok ? kJobVerify : kJobNone, (int)g, s, writer, false);
+        push(ok ? kJobVerify : kJobNone, (int)g, s, writer);
       }
     }
   }
@@ -153,7 +158,35 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
     *n_phases = 0;
     return CDPROBE_ERR_ARG;
   }
-  if (n > 0) phases[n - 1].sync_all = 1u;  // verdicts must be visible before the rows are written
+  // ---- closing barrier of every phase: who must this rank exchange flags with? -------------------
+  // The barrier between phase p and p + 1 has to order (a) the data dependencies — the verify that
+  // follows a write, the publication of write checksums — and (b) the exclusivity of NVLink ports the
+  // per-pair GB/s relies on: nobody may start loading a port that a transfer of the previous phase is
+  // still using.  With A(x, p) = the partner of rank x in phase p, the ranks whose phase-p or
+  // phase-(p+1) traffic shares a port with this rank's are
+  //     M = { A(g,p), A(g,p+1), A(A(g,p+1), p), A(A(g,p), p+1) }
+  // (symmetric: y in M(g) <=> g in M(y), so every rank waited for also signals).  An all-rank exchange
+  // (round 1: 15 of them at N = 8, 6-10 us each) is kept at the open and at the close of a run, and
+  // everywhere with CDPROBE_FLAG_ALL_RANK_BARRIERS.
+  const uint32_t everyone = (pl.n >= 32 ? 0xffffffffu : ((1u << pl.n) - 1u)) & ~(1u << g);
+  auto partner_in = [&](int round, int x) -> int {
+    return (round >= 0 && x >= 0) ? (int)pl.partner[round][x] : -1;
+  };
+  for (uint32_t p = 0; p < n; ++p) {
+    uint32_t m = 0;
+    if (p + 1 == n) {
+      m = everyone;  // verdicts must be visible before the rows are written
+    } else if ((in.flags & CDPROBE_FLAG_ALL_RANK_BARRIERS) && (phase_round[p] >= 0 || phase_round[p + 1] >= 0)) {
+      m = everyone;
+    } else {
+      const int r0 = phase_round[p], r1 = phase_round[p + 1];
+      const int a = partner_in(r0, (int)g), b = partner_in(r1, (int)g);
+      const int cand[4] = {a, b, partner_in(r0, b), partner_in(r1, a)};
+      for (int c : cand)
+        if (c >= 0 && (uint32_t)c != g) m |= 1u << c;
+    }
+    phases[p].sync_mask = m;
+  }
   *n_phases = n;
   uint32_t mask = 0;
   for (uint32_t j = 0; j < pl.n; ++j)
@@ -199,7 +232,8 @@ extern "C" int cdprobe_schedule(uint32_t n, uint32_t rank, uint64_t bytes, uint3
       out->cta0[jb][p] = j.cta0;
       out->nctas[jb][p] = j.nctas;
     }
-    out->sync_all[p] = (uint8_t)ph[p].sync_all;
+    out->sync_mask[p] = (uint16_t)(ph[p].sync_mask & mask);
+    out->sync_all[p] = (uint8_t)(mask != 0 && (ph[p].sync_mask & mask) == mask);
   }
   return CDPROBE_OK;
 }

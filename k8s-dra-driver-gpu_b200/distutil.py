@@ -46,6 +46,14 @@ class RankGroup:
     def min(self, x: float) -> float:
         return self._reduce(x, self.dist.ReduceOp.MIN) if self.dist is not None else float(x)
 
+    def gather_objects(self, obj):
+        """Every rank's small picklable object, in rank order, on every rank."""
+        if self.dist is None:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
     def session(self, prefix: str = "bench") -> str:
         """A rendezvous name every rank of this launch derives identically."""
         return f"{prefix}-{os.environ.get('MASTER_PORT', '0')}-{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}"

@@ -43,8 +43,8 @@ class Config:
     timeout_ms: int = 5000
     flags: int = 0
     seed: int = 0
-    min_fraction: float = 0.0  # 0 = library default (0.65 of link_peak_gbps)
-    link_peak_gbps: float = 900.0
+    min_fraction: float = 0.0  # 0 = library default (0.90 of the calibrated reference; 0.65 of an explicit peak)
+    link_peak_gbps: float = 0.0  # 0 = calibrated reference (include/cdprobe.h); > 0 = absolute GB/s
     ctas: int = 0
     world_size: int = 1
     rank: int = 0
@@ -101,6 +101,10 @@ class Result:
     event_ms: List[float]
     min_gbps_read: float
     min_gbps_write: float
+    gate_gbps_read: float = 0.0
+    gate_gbps_write: float = 0.0
+    unreachable_pairs: int = 0
+    slow_pairs: int = 0
     raw: abi.ResultT = dataclasses.field(repr=False, default=None)
 
     @property
@@ -141,6 +145,10 @@ class Result:
             event_ms=list(r.event_ms)[:n],
             min_gbps_read=r.min_gbps_read,
             min_gbps_write=r.min_gbps_write,
+            gate_gbps_read=r.gate_gbps_read,
+            gate_gbps_write=r.gate_gbps_write,
+            unreachable_pairs=r.unreachable_pairs,
+            slow_pairs=r.slow_pairs,
             raw=r,
         )
 
@@ -196,7 +204,7 @@ class Probe:
             _raise(self._lib, rc, "cdprobe_trace")
         names = {0: "-", 1: "read", 2: "write", 3: "verify", 4: "warm"}
         return [{"job0": names[t.kind0[p]], "peer0": t.peer0[p], "job1": names[t.kind1[p]], "peer1": t.peer1[p],
-                 "sync_all": int(t.sync_all[p]), "t_start": t.t_start[p], "t_end0": t.t_end0[p], "t_end1": t.t_end1[p],
+                 "sync_all": int(t.sync_all[p]), "sync_mask": int(t.sync_mask[p]), "t_start": t.t_start[p], "t_end0": t.t_end0[p], "t_end1": t.t_end1[p],
                  "t_arrive": t.t_arrive[p]} for p in range(t.n_phases)]
 
     def SetOption(self, option: int, value: int) -> None:
@@ -213,6 +221,21 @@ class Probe:
         rc = self._lib.cdprobe_remap_peer(self._h, local, peer)
         if rc != abi.OK:
             _raise(self._lib, rc, "cdprobe_remap_peer")
+
+    def CeCopy(self, copies, push: bool = True, nbytes: int = 0, reps: int = 4):
+        """Copy-engine reference on the probe's buffers: `copies` = [(local rank, peer rank), ...] run concurrently;
+        returns [(ms for `reps` copies, GB/s), ...].  Not part of a probe: the same-box ceiling quoted beside it."""
+        k = len(copies)
+        loc = (C.c_uint32 * k)(*[c[0] for c in copies])
+        peer = (C.c_uint32 * k)(*[c[1] for c in copies])
+        ms = (C.c_double * k)()
+        rc = self._lib.cdprobe_ce_copy(self._h, k, loc, peer, 1 if push else 0, nbytes, reps, ms)
+        if rc != abi.OK:
+            _raise(self._lib, rc, "cdprobe_ce_copy")
+        info = self.Info()
+        pl = plan(info.n, self.cfg.bytes, self.cfg.mode, self.cfg.flags)
+        nb = min(x for x in (nbytes or pl.src_bytes, pl.src_bytes, pl.land_bytes))
+        return [(ms[i], nb * reps / (ms[i] * 1e-3) / 1e9 if ms[i] > 0 else 0.0) for i in range(k)]
 
     def Corrupt(self, local: int, byte_offset: int, xor_mask: int) -> None:
         rc = self._lib.cdprobe_corrupt(self._h, local, byte_offset, xor_mask)

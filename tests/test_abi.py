@@ -30,7 +30,7 @@ def test_exports_every_declared_symbol(pkg):
 
 def test_abi_version_and_strerror(pkg):
     lib = pkg.abi.load_library()
-    assert lib.cdprobe_abi_version() == pkg.abi.ABI_VERSION == 1
+    assert lib.cdprobe_abi_version() == pkg.abi.ABI_VERSION == 2
     assert lib.cdprobe_strerror(0) == b"ok"
     for code in range(-10, 0):
         assert lib.cdprobe_strerror(code) not in (b"", b"unknown cdprobe error")

@@ -127,3 +127,135 @@ def test_run_once_writes_a_passing_verdict_and_check_reads_it(tmp_path):
     assert "nvidia_dra_fabric_probe_duration_seconds" in prom and "nvidia_dra_fabric_probe_unreachable_pairs 0" in prom
     assert prom.count("nvidia_dra_fabric_probe_pair_gbps{") == 2 * (n * (n - 1) if n > 1 else 1)
     assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": str(v)}).returncode == 0
+
+
+# ---- round 2: one verdict schema for the Go patch and the C++ twin; stale verdicts; signals ------------
+GO_DAEMON = os.path.join(ROOT, "integration", "cmd", "compute-domain-daemon", "fabricprobe.go")
+GO_JSON_TYPE = {"int": int, "int64": int, "uint64": int, "bool": bool, "float32": (int, float), "float64": (int, float),
+                "string": str, "[]int": (list, int), "[]float32": (list, (int, float))}
+
+
+def go_verdict_schema():
+    """{json key: python type} parsed from the struct tags of fabricProbeVerdict in the Go patch."""
+    import re
+
+    src = open(GO_DAEMON).read()
+    body = src[src.index("type fabricProbeVerdict struct {"):]
+    body = body[:body.index("\n}")]
+    fields = re.findall(r"^\s*(\w+)\s+(\S+)\s+`json:\"(\w+)\"`", body, re.M)
+    assert len(fields) >= 15
+    return {tag: GO_JSON_TYPE[typ] for _, typ, tag in fields}
+
+
+@pytest.mark.parametrize("ok", ["ok", "bad"])
+def test_cpp_verdict_matches_the_go_struct_key_for_key(tmp_path, ok):
+    """the Go `check` must be able to read what the C++ `run` wrote and vice versa —
+    same keys, same JSON types (reach cells are integers on both sides, min GB/s are carried)."""
+    v = tmp_path / "fabricprobe.json"
+    assert daemon(["selftest-verdict", str(v), ok], {"POD_UID": "pod-123"}).returncode == 0
+    d = json.loads(v.read_text())
+    schema = go_verdict_schema()
+    assert set(d) == set(schema), (set(d) ^ set(schema))
+    for key, typ in schema.items():
+        if isinstance(typ, tuple) and typ[0] is list:
+            assert isinstance(d[key], list) and all(isinstance(x, typ[1]) and not isinstance(x, bool) for x in d[key]), key
+        else:
+            assert isinstance(d[key], typ), key
+            if typ is int:
+                assert not isinstance(d[key], bool), key
+    assert d["schema"] == 2 and d["pod_uid"] == "pod-123" and d["ok"] is (ok == "ok") and d["n"] == 2
+    assert d["reach_write"] == ([1, 1, 1, 1] if ok == "ok" else [1, 0, 0, 1])
+    assert d["min_gbps_read"] == pytest.approx(671.5) and d["gate_gbps_write"] == pytest.approx(625.7)
+    # and the C++ check reads it back with the numbers in the message (they were always 0 in round 1's Go text)
+    r = daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": str(v), "POD_UID": "pod-123"})
+    if ok == "ok":
+        assert r.returncode == 0
+    else:
+        assert r.returncode == 1
+        assert "fabric probe failed: 2 unreachable pair(s), 0 slow pair(s), min read 672 GB/s, min write 702 GB/s: synthetic" in r.stderr
+
+
+def test_go_patch_is_internally_consistent():
+    """The Go files cannot be compiled here; at least every identifier the daemon patch uses from the shim,
+    the gate and the metrics package exists there with the name and arity it is called with."""
+    import re
+
+    d = open(GO_DAEMON).read()
+    shim = open(os.path.join(ROOT, "integration", "pkg", "fabricprobe", "fabricprobe.go")).read()
+    stub = open(os.path.join(ROOT, "integration", "pkg", "fabricprobe", "fabricprobe_stub.go")).read()
+    gate = open(os.path.join(ROOT, "integration", "pkg", "featuregates", "fabricprobe_gate.go")).read()
+    met = open(os.path.join(ROOT, "integration", "pkg", "metrics", "fabricprobe.go")).read()
+    for name in set(re.findall(r"\bfabricprobe\.([A-Z]\w+)", re.sub(r"//.*", "", d))):
+        assert re.search(rf"\b{name}\b", shim), f"pkg/fabricprobe lacks {name}"
+        assert re.search(rf"\b{name}\b", stub), f"the !cgo stub lacks {name}"
+    for fld in set(re.findall(r"\bres\.(\w+)", d)):
+        assert re.search(rf"\b{fld}\b", shim[shim.index("type Result struct"):shim.index("type Probe struct")]), fld
+        assert re.search(rf"\b{fld}\b", stub[stub.index("type Result struct"):stub.index("type Probe struct")]), fld
+    for fld in set(re.findall(r"fabricprobe\.Config\{([^}]*)\}", d, re.S)[0].split()):
+        if fld.endswith(":"):
+            assert re.search(rf"\b{fld[:-1]}\b", shim[shim.index("type Config struct"):shim.index("type Result struct")]), fld
+    assert "FabricProbe featuregate.Feature" in gate and "featuregates.FabricProbe" in d
+    assert "func ObserveFabricProbe(node string, d time.Duration, ok bool, unreachable, slow, n int, gbpsRead, gbpsWrite []float32)" in met
+    assert len(re.findall(r"metrics\.ObserveFabricProbe\(([^)]*)\)", d)[0].split(",")) == 8
+    # the update channel keeps its single receiver (ADVICE r01): the patch never receives from it
+    assert "GetDaemonInfoUpdateChan()" not in re.sub(r"//.*", "", d)
+    # every C symbol the shim binds is one the header declares
+    hdr = open(os.path.join(ROOT, "include", "cdprobe.h")).read()
+    for sym in set(re.findall(r'dlsym\(cdp_dl, "(\w+)"\)', shim)):
+        assert f" {sym}(" in hdr, sym
+    for fld in set(re.findall(r"\br\.(\w+)", shim)) | set(re.findall(r"\bc\.(\w+) = ", shim)):
+        assert re.search(rf"\b{fld}\b", hdr), f"cdprobe.h has no field {fld}"
+
+
+def test_check_ignores_a_verdict_it_does_not_own(tmp_path):
+    """/imexd outlives pods.  A failing verdict stamped by another pod, or from before a reboot,
+    must not keep this pod NotReady (and a passing one must not make it Ready — it is simply not there)."""
+    other = verdict(tmp_path, False, unreachable=3, pod_uid="pod-old", boot_id="")
+    assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": other, "POD_UID": "pod-new"}).returncode == 0
+    assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": other, "POD_UID": "pod-old"}).returncode == 1
+    rebooted = verdict(tmp_path, False, unreachable=3, pod_uid="", boot_id="00000000-dead-beef-0000-000000000000")
+    assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": rebooted}).returncode == 0
+    # periodic re-probe configured => a verdict must keep coming (default max age 3 x interval + 60 s)
+    old = verdict(tmp_path, True, time_unix=1000)
+    r = daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": old, "FABRIC_PROBE_INTERVAL_S": "10"})
+    assert r.returncode == 1 and "stale" in r.stderr
+
+
+@pytest.mark.skipif(gpu_count() > 0, reason="CPU-only behaviour")
+def test_run_removes_a_stale_verdict_at_startup(tmp_path):
+    """A verdict left in the mount by a previous pod is gone once `run` has started, even when the probe turns
+    out to be unsupported on this node (round 1 left a stale ok:false in place forever)."""
+    v = tmp_path / "fabricprobe.json"
+    v.write_text(json.dumps({"ok": False, "unreachable_pairs": 9, "time_unix": 5}))
+    r = daemon(["run", "--once"], {"COMPUTE_DOMAIN_UUID": "cd-1", "CDPROBE_LIBRARY": LIB, "FABRIC_PROBE_VERDICT_PATH": str(v)})
+    assert r.returncode == 0 and not v.exists()
+
+
+@pytest.mark.gpu
+def test_run_loop_reprobes_on_sigusr1_and_exits_on_sigterm(tmp_path):
+    """The daemon loop itself: first pass at start, another on SIGUSR1 (the stand-in for a daemon-set update),
+    SIGTERM ends it — signals are only deliverable inside the wait, so none is lost."""
+    import signal
+    import time
+
+    v = tmp_path / "fabricprobe.json"
+    env = {"PATH": os.environ.get("PATH", ""), "LD_LIBRARY_PATH": os.environ.get("LD_LIBRARY_PATH", ""),
+           "COMPUTE_DOMAIN_UUID": "cd-1", "CDPROBE_LIBRARY": LIB, "FABRIC_PROBE_VERDICT_PATH": str(v),
+           "FABRIC_PROBE_BYTES": str(64 << 20), "POD_UID": "pod-7"}
+    p = subprocess.Popen([DAEMON, "run"], env=env, stderr=subprocess.PIPE, text=True)
+    try:
+        t_end = time.time() + 240
+        while not v.exists() and time.time() < t_end:
+            time.sleep(0.1)
+        first = json.loads(v.read_text())
+        assert first["ok"] is True and first["pod_uid"] == "pod-7"
+        for k in range(3):  # a burst: the second and third may coalesce, none may be lost for good
+            p.send_signal(signal.SIGUSR1)
+        time.sleep(2.0)
+        p.send_signal(signal.SIGTERM)
+        err = p.communicate(timeout=60)[1]
+    finally:
+        if p.poll() is None:
+            p.kill()
+    assert p.returncode == 0 and "Exiting" in err
+    assert err.count("t_fabric_probe") >= 2

@@ -430,3 +430,184 @@ def test_nvml_oracle_runs_on_this_box(oracle):
     assert o.n >= 1 and o.nvml_calls >= 18 * o.n
     assert all(o.reach[i * 16 + i] == 1 for i in range(o.n))
     assert o.cc_major[0] == 10
+
+
+# ------------------------------------------------------ round 2: gate, barriers, abort drain ----
+def _cells(n):
+    return [(i, j) for i in range(n) for j in range(n) if i != j]
+
+
+def test_bandwidth_gate_fails_a_slow_but_reachable_domain(pkg, oracle):
+    """The bandwidth branch of the verdict: with a gate nobody can meet every pair is
+    reachable yet the verdict is NotReady, counted as slow — not unreachable — pairs; with the gate lowered
+    the same handle passes.  Same-device ranks, so it runs on a 1-GPU box."""
+    n, nbytes = 3, 4 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000,
+                             min_fraction=0.99, link_peak_gbps=1e6)) as p:
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+        assert r.reach == [[1] * n for _ in range(n)] and not r.aborted
+        assert not r.verdict and r.slow_pairs == n * (n - 1) and r.unreachable_pairs == 0
+        assert r.gate_gbps_read == pytest.approx(0.99e6, rel=1e-5) and r.gate_gbps_write == pytest.approx(0.99e6, rel=1e-5)
+        p.SetOption(pkg.abi.OPT_LINK_PEAK_MBPS, 1)          # 0.001 GB/s x 0.99: everything passes
+        r = p.Run()
+        assert r.verdict and r.slow_pairs == 0 and r.unreachable_pairs == 0
+        # the calibrated reference: 0.90 x bytes_per_pair / (bytes_per_pair / 672 GB/s + 8 us) for bidirectional reads
+        p.SetOption(pkg.abi.OPT_LINK_PEAK_MBPS, 0)
+        p.SetOption(pkg.abi.OPT_MIN_FRACTION_PPM, 0)
+        r = p.Run()
+        bpp = r.bytes_per_pair
+        assert r.gate_gbps_read == pytest.approx(0.90 * bpp / (bpp / 672.0 + 8000.0), rel=1e-4)
+        assert r.gate_gbps_write == pytest.approx(0.90 * bpp / (bpp / 703.0 + 8000.0), rel=1e-4)
+
+
+def test_throttled_issuer_fails_only_its_own_pairs(pkg, oracle):
+    """A rank whose transfers crawl (1 CTA instead of 8) drags only the pairs IT issues under a gate placed
+    between the two speeds; the other ranks' rows stay at speed and the matrices stay all-ones."""
+    n, nbytes = 3, 16 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000,
+                             min_fraction=1.0, link_peak_gbps=1e-3)) as p:
+        p.SetOption(pkg.abi.OPT_CTAS_RANK, (1 << 16) | 1)  # local rank 0 -> one CTA
+        assert p.Info().ctas[0] == 1 and p.Info().ctas[1] == 8
+        p.Run()
+        rs = [p.Run() for _ in range(3)]
+        slow = max(max(r.gbps_read[0][j], r.gbps_write[0][j]) for r in rs for j in range(1, n))
+        fast = min(min(r.gbps_read[i][j], r.gbps_write[i][j]) for r in rs for i in range(1, n) for j in range(n) if i != j)
+        if fast < 1.5 * slow:
+            pytest.skip(f"no clean separation on this box (slow {slow:.0f}, fast {fast:.0f} GB/s)")
+        thr = (slow * fast) ** 0.5
+        p.SetOption(pkg.abi.OPT_LINK_PEAK_MBPS, int(thr * 1e3))
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+        assert r.reach == [[1] * n for _ in range(n)]
+        assert not r.verdict and r.unreachable_pairs == 0 and r.slow_pairs == n - 1  # exactly row 0
+        for i, j in _cells(n):
+            under = r.gbps_read[i][j] < thr or r.gbps_write[i][j] < thr
+            assert under == (i == 0), (i, j, r.gbps_read[i][j], r.gbps_write[i][j], thr)
+
+
+@pytest.mark.parametrize("n", [2, 4, 5])
+def test_neighbourhood_and_all_rank_barriers_agree(pkg, oracle, n):
+    """Default (neighbourhood) barriers and the round-1 all-rank exchange give the same bits and checksums."""
+    nbytes = 2 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
+        for all_rank in (0, 1, 0):
+            p.SetOption(pkg.abi.OPT_ALL_RANK_BARRIERS, all_rank)
+            tr = p.Trace(0) if all_rank else None
+            for _ in range(3):
+                r = p.Run()
+                check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+                assert r.reach == [[1] * n for _ in range(n)] and not r.aborted
+            tr = p.Trace(0)
+            if n > 2:
+                remote = [t for t in tr[:-1] if t["job0"] in ("read", "write", "warm")]
+                assert all(bool(t["sync_all"]) == bool(all_rank) for t in remote if t["sync_mask"])
+            assert tr[-1]["sync_all"] == 1
+
+
+def test_abort_in_the_middle_of_a_transfer_drains_and_recovers(pkg, oracle):
+    """The device watchdog firing while TMA loads are in flight: the kernel drains what
+    it issued and exits cleanly, the call reports the timeout, and the same handle then runs at parity."""
+    n, nbytes = 2, 512 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=4, timeout_ms=20000)) as p:
+        ok = p.Run()
+        assert ok.reach == [[1] * n for _ in range(n)]
+        assert min(ok.device_ms) > 2.0  # the run is long enough for a 1 ms deadline to land inside a phase
+        p.SetOption(pkg.abi.OPT_TIMEOUT_MS, 1)
+        r = p.Run(allow_timeout=True)
+        assert r.aborted and not r.verdict
+        p.SetOption(pkg.abi.OPT_TIMEOUT_MS, 20000)
+        for _ in range(2):
+            good = p.Run()
+            assert not good.aborted
+            check_full_parity(pkg, oracle, good, n, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
+def test_run_never_leaves_the_result_as_it_came_in(pkg):
+    """cdprobe_run fills the whole result before anything can fail (the daemon writes its verdict
+    from it whatever the return code), so garbage in the caller's buffer never survives a call."""
+    import ctypes as C
+
+    n, nbytes = 2, 1 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
+        out = pkg.abi.ResultT()
+        C.memset(C.byref(out), 0xAB, C.sizeof(out))
+        assert p.run_raw(out) == pkg.abi.OK and out.n == n and out.verdict in (0, 1)
+        assert out.abi == pkg.abi.ABI_VERSION and out.reserved1 == 0 and out.aborted == 0
+
+
+def test_solo_rank_runs_alone_and_reads_at_parity(pkg, oracle):
+    """The profiling mode ncu replays (one self-contained kernel, no cross-GPU barrier): the solo rank's reads
+    still carry the oracle's checksums; nobody verifies its writes, so reach_write stays 0."""
+    n, nbytes = 2, 8 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
+        p.Run()
+        p.SetOption(pkg.abi.OPT_SOLO_RANK, 1)
+        r = p.Run()
+        assert r.launches == 1 and not r.aborted and not r.verdict
+        assert r.reach_read[0][1] == 1 and r.reach_write[0][1] == 0
+        assert (r.sum_read[0][1], r.xor_read[0][1]) == expected_read(oracle, n, nbytes, 1, 0, 1)
+        assert (r.sum_write[0][1], r.xor_write[0][1]) == oracle.write_checksum(SEED, 0, 1, r.run_seq, r.bytes_per_pair // 8)
+        p.SetOption(pkg.abi.OPT_SOLO_RANK, 0)
+        r = p.Run()
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
+def test_copy_engine_reference_runs_on_the_probe_buffers(pkg, oracle):
+    n, nbytes = 2, 64 << 20
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
+        (ms, gbps), = p.CeCopy([(0, 1)], push=True, reps=3)
+        assert ms > 0 and gbps > 10
+        both = p.CeCopy([(0, 1), (1, 0)], push=False, reps=3)
+        assert len(both) == 2 and all(g > 10 for _, g in both)
+        r = p.Run()  # the copies scribbled over landing slots: a probe rewrites them before it verifies
+        check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
+
+
+@pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
+def test_default_gate_passes_healthy_nvlink_and_catches_a_throttled_rank(pkg, oracle):
+    """On real peers, 1 GiB per GPU: the calibrated default gate (0.90 of the healthy SM-path figure) passes,
+    a rank throttled to 2 CTAs fails exactly the pairs it issues, and the copy engine gives the ceiling."""
+    n = min(NGPU, 8)
+    with pkg.Open(pkg.Config(ordinals=list(range(n)), bytes=1 << 30, timeout_ms=20000)) as p:
+        p.Run()
+        r = p.Run()
+        assert r.verdict and r.slow_pairs == 0 and r.unreachable_pairs == 0, (r.min_gbps_read, r.min_gbps_write)
+        assert 500 < r.gate_gbps_read < 672 and 500 < r.gate_gbps_write < 703
+        assert r.min_gbps_read > r.gate_gbps_read and r.min_gbps_write > r.gate_gbps_write
+        p.SetOption(pkg.abi.OPT_CTAS_RANK, (1 << 16) | 2)
+        p.Run()
+        t = p.Run()
+        assert t.reach == [[1] * n for _ in range(n)] and not t.verdict
+        assert t.slow_pairs == n - 1 and t.unreachable_pairs == 0
+        assert all(t.gbps_read[0][j] < t.gate_gbps_read for j in range(1, n))
+        assert all(t.gbps_read[i][j] >= t.gate_gbps_read for i in range(1, n) for j in range(n) if i != j)
+        p.SetOption(pkg.abi.OPT_CTAS_RANK, (1 << 16) | 148)
+        (ms, uni), = p.CeCopy([(0, 1)], push=True, reps=4)
+        bidi = p.CeCopy([(0, 1), (1, 0)], push=True, reps=4)
+        assert uni > 600 and min(g for _, g in bidi) > 600
+
+
+def test_topology_agrees_with_the_oracle_on_the_real_nvml(pkg, oracle):
+    """a12 / n2 on the box's own libnvidia-ml.so.1 (not the fake): UUID order, MIG flags, active NVLink
+    counts, fabric state and clique id (strict and legacy) equal the oracle's restatement of
+    nvlib.go:195-363 / go-nvlib device.go:464-495."""
+    for strict, flags in ((True, 0), (False, 1)):
+        t = pkg.topology(strict=strict)
+        o = oracle.nvml_poll(0, flags | 4)  # no imex-ctl exec: the device + clique walk
+        assert t.n == o.n >= 1
+        assert [t.uuid[i].value.decode() for i in range(t.n)] == o.uuids()
+        assert [t.pci_bus_id[i].value.decode() for i in range(t.n)] == [o.pci_bus_id[i].value.decode() for i in range(o.n)] \
+            or all(not o.pci_bus_id[i].value for i in range(o.n))
+        assert list(t.mig)[:t.n] == list(o.mig_enabled)[:o.n]
+        assert list(t.links_active)[:t.n] == list(o.n_links)[:o.n]
+        assert list(t.fabric_state)[:t.n] == list(o.fabric_state)[:o.n]
+        assert t.clique_id.decode() == o.clique_id.decode()
+        assert bool(t.clique_error) == bool(o.clique_err)
+        if t.clique_error:
+            assert t.clique_error.decode() == o.clique_err_text.decode()
+    # and the CUDA side names the same devices: every probe rank's UUID is one NVML enumerated
+    with pkg.Open(pkg.Config(ordinals=None, bytes=1 << 20, mode=pkg.abi.MODE_REACH_ONLY, timeout_ms=20000)) as p:
+        info = p.Info()
+        nv = set(o.uuids())
+        assert all(info.uuid[i].value.decode() in nv for i in range(info.n_local))

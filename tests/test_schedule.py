@@ -2,7 +2,9 @@
 GPU through cdprobe_schedule().  These are the properties the device barrier and the parity of the
 matrices rely on:
 
-  * every rank has the same number of phases and the same barrier kinds at every index;
+  * every rank has the same number of phases; the flag exchange that closes a phase is symmetric
+    (i waits for j <=> j signals i), spans every rank at the end of a run, and always contains every
+    rank whose transfers share an NVLink port with this rank's on either side of the barrier;
   * in a phase a rank touches at most one peer over NVLink and is touched by at most one
     (exclusive endpoints), and the pairing follows the tournament plan;
   * every ordered pair is read exactly once and written exactly once per run;
@@ -16,7 +18,7 @@ import itertools
 import pytest
 
 NONE, READ, WRITE, VERIFY, WARM = 0, 1, 2, 3, 4
-UNI, SERIAL, DIAG = 0x80, 0x100, 0x04
+UNI, SERIAL, DIAG, ALLRANK = 0x80, 0x100, 0x04, 0x400
 
 
 def schedule(pkg, n, rank, mode=1, ops=3, flags=0, ctas=148, vctas=32, nbytes=1 << 30):
@@ -39,7 +41,7 @@ def slot_of(i, j):
     return i if i < j else i - 1
 
 
-CASES = [dict(flags=f, ops=o, ctas=c) for f in (0, UNI, SERIAL, UNI | SERIAL, DIAG, UNI | DIAG)
+CASES = [dict(flags=f, ops=o, ctas=c) for f in (0, UNI, SERIAL, UNI | SERIAL, DIAG, UNI | DIAG, ALLRANK, ALLRANK | UNI)
          for o in (1, 2, 3) for c in (148, 8)]
 
 
@@ -55,12 +57,31 @@ def test_schedule_invariants(pkg, n, case):
     plan = pkg.plan(n, 1 << 30, 1, flags & DIAG)
     np_ = tabs[0].n_phases
     assert np_ <= pkg.abi.MAX_PHASES
-    # same length and barrier kinds on every rank; the last barrier spans all ranks
-    for t in tabs:
-        assert t.n_phases == np_
-        assert list(t.sync_all)[:np_] == list(tabs[0].sync_all)[:np_]
-    if np_:
-        assert tabs[0].sync_all[np_ - 1] == 1
+    # same length on every rank; the last barrier spans all ranks; the exchange is symmetric
+    everyone = [((1 << n) - 1) & ~(1 << r) for r in range(n)]
+    for r, t in enumerate(tabs):
+        assert t.n_phases == np_ and t.peer_mask == everyone[r]
+        for ph in range(np_):
+            assert t.sync_mask[ph] & ~everyone[r] == 0
+            assert t.sync_all[ph] == (1 if n > 1 and t.sync_mask[ph] == everyone[r] else 0)
+            for j in range(n):
+                assert bool(t.sync_mask[ph] >> j & 1) == bool(tabs[j].sync_mask[ph] >> r & 1), "asymmetric barrier"
+    if np_ and n > 1:
+        assert all(t.sync_all[np_ - 1] == 1 for t in tabs)
+    # ports[ph][r] = the ranks whose NVLink ports rank r's phase-ph transfer loads (both ends of its pair,
+    # whoever issues); a transfer of phase ph + 1 may only start once every transfer of phase ph that shares
+    # a port with it is over, i.e. its rank must be in the closing exchange of phase ph
+    ports = [[set() for _ in range(n)] for _ in range(np_)]
+    for ph in range(np_):
+        for r, t in enumerate(tabs):
+            if t.kind[0][ph] in (READ, WRITE, WARM) and t.peer[0][ph] != r:
+                ports[ph][r] |= {r, t.peer[0][ph]}
+                ports[ph][t.peer[0][ph]] |= {r, t.peer[0][ph]}
+    for ph in range(np_ - 1):
+        for x in range(n):
+            for y in range(n):
+                if x != y and ports[ph + 1][x] & ports[ph][y]:
+                    assert tabs[x].sync_mask[ph] >> y & 1, f"phase {ph}: rank {x} may start while {y} still uses its port"
     reads, writes, verifies = {}, {}, {}
     for ph in range(np_):
         touched_by = {}
@@ -72,7 +93,9 @@ def test_schedule_invariants(pkg, n, case):
                 assert 0 <= p < n
                 assert p not in touched_by, "two ranks hit the same peer in one phase"
                 touched_by[p] = r
-                assert t.sync_all[ph] == 1  # remote traffic is always closed by an all-rank barrier
+                assert t.sync_mask[ph] >> p & 1  # a pair always closes its transfer together
+                if flags & ALLRANK:
+                    assert t.sync_all[ph] == 1  # round-1 behaviour: remote traffic closed by an all-rank barrier
                 # the pairing is the tournament's: p's partner in that round is r
                 assert any(plan.partner[rd][r] == p for rd in range(plan.rounds))
                 if not (flags & UNI) and k0 != WARM:
@@ -114,6 +137,8 @@ def test_schedule_invariants(pkg, n, case):
         assert set(verifies) == set(writes)  # every written slot is verified exactly once, by its owner
         for (w, o), (ph, slot) in verifies.items():
             assert ph > writes[(w, o)] or (w == o and ph > writes[(w, o)])
+            if w != o:  # the owner learns of the write (and its published checksum) at the write phase's own barrier
+                assert tabs[o].sync_mask[writes[(w, o)]] >> w & 1
             assert slot == (slot_of(w, o) if w != o else n - 1)
     else:
         assert not writes and not verifies
@@ -129,6 +154,14 @@ def test_default_8gpu_table_shape(pkg):
     assert [t.kind[1][p] for p in range(1, 15)] == [NONE, VERIFY] * 7
     assert all(t.nctas[0][p] == 148 - 32 and t.cta0[1][p] == 116 and t.nctas[1][p] == 32 for p in range(2, 15, 2))
     assert t.peer_mask == 0xFF & ~(1 << 3)
+    # neighbourhood barriers: one all-rank exchange (the last); a write -> read barrier inside a round is the
+    # pair alone; between rounds at most 4 ranks
+    for t in tabs:
+        assert [t.sync_all[p] for p in range(15)] == [0] * 14 + [1]
+        assert all(bin(t.sync_mask[p]).count("1") == 1 for p in [0] + list(range(1, 14, 2)))  # warm->W(0), W(r)->R(r)
+        assert all(2 <= bin(t.sync_mask[p]).count("1") <= 4 for p in range(2, 14, 2))          # R(r) -> W(r+1)
+    rc, old = table(pkg, 8, flags=ALLRANK)
+    assert rc == 0 and all(old[0].sync_all[p] == 1 for p in range(15))
 
 
 def test_overlap_needs_enough_ctas(pkg):
