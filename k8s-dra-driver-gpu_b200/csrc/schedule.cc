@@ -48,17 +48,23 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
     set_job(p.job[0], kind, peer, slot, writer, 0, ctas);
     return p;
   };
-  const uint32_t vctas = in.verify_ctas;
+  // Overlapped verify is a property of the DOMAIN's schedule (every rank must walk the same number of phases),
+  // so it may not depend on this rank's CTA count — a rank throttled to 2 CTAs next to 148-CTA peers once
+  // fell back to serial verify on its own, grew extra phases and dead-locked the barrier sequence.  Only the
+  // split adapts: verify_ctas when there is room, half the CTAs on a small grid, and on a single CTA both
+  // jobs cover CTA 0 (the kernel runs a CTA's jobs one after the other).
   const bool overlap = (in.flags & CDPROBE_FLAG_OVERLAP_VERIFY) && (ops & CDPROBE_OP_WRITE) && pl.rounds > 0 &&
-                       vctas > 0 && ctas >= 2 * vctas;
+                       in.verify_ctas > 0;
+  const uint32_t vctas = ctas >= 2 * in.verify_ctas ? in.verify_ctas : (ctas >= 2 ? ctas / 2 : ctas);
+  const uint32_t link_ctas = ctas >= 2 ? ctas - vctas : ctas;  // CTAs of the NVLink job when a verify rides along
   struct Pending {
     bool have = false, ok = false;
     uint32_t slot = 0, writer = 0;
   } pend;
   auto attach = [&](Phase& p) {  // give the tail CTAs of phase p the pending verify
     if (!pend.have) return;
-    if (p.job[0].kind != kJobNone) p.job[0].nctas = (uint16_t)(ctas - vctas);
-    set_job(p.job[1], pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, ctas - vctas, vctas);
+    if (p.job[0].kind != kJobNone) p.job[0].nctas = (uint16_t)link_ctas;
+    set_job(p.job[1], pend.ok ? kJobVerify : kJobNone, (int)g, pend.slot, pend.writer, ctas >= 2 ? link_ctas : 0, vctas);
     pend.have = false;
   };
   // Bidirectional (default): both ranks of a pair issue at once, so every NVLink port carries
@@ -112,7 +118,7 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
   // (both jobs are HBM-bound, hence the near-even split).  One barrier fewer than read / write / verify.
   cur_round = -1;
   const bool diag_overlap = pl.diag && (in.flags & CDPROBE_FLAG_OVERLAP_VERIFY) && (ops & CDPROBE_OP_WRITE) &&
-                            (ops & CDPROBE_OP_READ) && ctas >= 2;
+                            (ops & CDPROBE_OP_READ);  // not a function of ctas: see `overlap` above
   if (pl.diag) {
     if (ops & CDPROBE_OP_WRITE) push(kJobWrite, (int)g, pl.diag_slot, 0);
     if (ops & CDPROBE_OP_READ) {
@@ -120,11 +126,15 @@ int make_phases(const ScheduleInput& in, Phase* phases, uint32_t* n_phases, uint
       if (diag_overlap) {
         // measured at N = 1 with an even split: the verify half (reading lines that were just written)
         // runs ~5 % slower than the source read, so it gets 33/64 of the CTAs (76 of 148)
-        uint32_t half = (ctas * 33u + 32u) / 64u;
-        if (half < 1) half = 1;
-        if (half >= ctas) half = ctas - 1;
-        ph.job[0].nctas = (uint16_t)(ctas - half);
-        set_job(ph.job[1], kJobVerify, (int)g, pl.diag_slot, g, ctas - half, half);
+        if (ctas >= 2) {
+          uint32_t half = (ctas * 33u + 32u) / 64u;
+          if (half < 1) half = 1;
+          if (half >= ctas) half = ctas - 1;
+          ph.job[0].nctas = (uint16_t)(ctas - half);
+          set_job(ph.job[1], kJobVerify, (int)g, pl.diag_slot, g, ctas - half, half);
+        } else {
+          set_job(ph.job[1], kJobVerify, (int)g, pl.diag_slot, g, 0, 1);  // one CTA: read, then verify
+        }
       }
     }
   }

@@ -493,15 +493,16 @@ def test_neighbourhood_and_all_rank_barriers_agree(pkg, oracle, n):
     with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
         for all_rank in (0, 1, 0):
             p.SetOption(pkg.abi.OPT_ALL_RANK_BARRIERS, all_rank)
-            tr = p.Trace(0) if all_rank else None
             for _ in range(3):
                 r = p.Run()
                 check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
                 assert r.reach == [[1] * n for _ in range(n)] and not r.aborted
             tr = p.Trace(0)
             if n > 2:
-                remote = [t for t in tr[:-1] if t["job0"] in ("read", "write", "warm")]
-                assert all(bool(t["sync_all"]) == bool(all_rank) for t in remote if t["sync_mask"])
+                # inside a round (write -> read of the same pair) the default exchange is the pair alone
+                inner = [t for t, nxt in zip(tr, tr[1:]) if t["job0"] == "write" and nxt["job0"] == "read" and t["peer0"] == nxt["peer0"]]
+                assert inner and all(bool(t["sync_all"]) == bool(all_rank) for t in inner)
+                assert all_rank or all(bin(t["sync_mask"]).count("1") == 1 for t in inner)
             assert tr[-1]["sync_all"] == 1
 
 
@@ -611,3 +612,53 @@ def test_topology_agrees_with_the_oracle_on_the_real_nvml(pkg, oracle):
         info = p.Info()
         nv = set(o.uuids())
         assert all(info.uuid[i].value.decode() in nv for i in range(info.n_local))
+
+
+# ---- faults: the KERNELS' matrix under an injected fault == the ORACLE's matrix under NVML's statement of it ----
+def _oracle_reach_for(tmp_path, scenario, n):
+    """The reachability matrix the oracle derives from a (fake) NVML that reports `scenario` (fresh process:
+    the fake library reads its script at load; reuses the harness of tests/test_oracle_nvml.py)."""
+    from test_oracle_nvml import poll
+
+    r = poll(tmp_path, scenario)
+    assert r["rc"] == 0 and r["n"] == n
+    return r["reach"]
+
+
+FAULTS = [
+    # (name, NVML scenario, kernel-side injection: list of (local rank, peer) mappings torn down, flags)
+    ("healthy", "gpus 4\n", [], 0),
+    ("p2p-disabled-pair", "gpus 4\np2p 1 2 nvlink 6\np2p 2 1 nvlink 6\n", [(1, 2)], 0),          # DISABLED_BY_REGKEY, both ways
+    ("p2p-read-and-write-off", "gpus 4\np2p 0 3 read 3\np2p 3 0 write 4\n", [(3, 0)], 0),
+    ("all-links-down-on-gpu-2", "gpus 4\n" + "".join(f"link_down 2 {l}\n" for l in range(18)), [(2, 0), (2, 1), (2, 3)], 0),
+    ("gpu-3-in-mig-mode", "gpus 4\nmig 3 1\n", [(3, 0), (3, 1), (3, 2)], 0),
+    ("every-gpu-a-mig-instance", "gpus 4\n" + "".join(f"mig {g} 1\n" for g in range(4)), [], 0x200),  # SIMULATE_MIG
+]
+
+
+@pytest.mark.parametrize("name,scenario,unmaps,flags", FAULTS, ids=[f[0] for f in FAULTS])
+def test_kernel_matrix_under_faults_equals_oracle_matrix(pkg, oracle, tmp_path, name, scenario, unmaps, flags):
+    """the boolean half of parity under faults used to be oracle vs the product's NVML
+    walk only.  Here the fault is injected on the DEVICE side (mappings torn down: the loads/stores of that
+    pair cannot happen; MIG: no peer mapping at all) and the matrix the kernels produce must equal, bit for
+    bit, the matrix the oracle computes from an NVML that reports the same fault (link down on every link of
+    a GPU, P2P disabled for a pair, MIG mode).  The kernels treat a pair as one unit — a torn mapping in
+    either direction zeroes both cells — so the NVML scenarios state the fault for both ordered pairs."""
+    n, nbytes = 4, 1 << 20
+    exp = _oracle_reach_for(tmp_path, scenario, n)
+    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME | flags, ctas=8, timeout_ms=20000)) as p:
+        for local, peer in unmaps:
+            p.UnmapPeer(local, peer)
+        r = p.Run()
+        assert not r.aborted
+        assert r.reach == exp, (name, r.reach, exp)
+        healthy = all(all(c == 1 for c in row) for row in exp)
+        mig_only = bool(flags & 0x200)
+        assert r.verdict == (healthy or mig_only)  # a MIG-only domain is "not applicable", not a failure (SURVEY H8)
+        if not mig_only:
+            assert r.unreachable_pairs == sum(1 for i in range(n) for j in range(n) if i != j and not exp[i][j])
+        # cells that are still reachable carry the oracle's checksums
+        for i in range(n):
+            for j in range(n):
+                if i != j and exp[i][j]:
+                    assert (r.sum_read[i][j], r.xor_read[i][j]) == expected_read(oracle, n, nbytes, 1, i, j)
