@@ -335,7 +335,7 @@ def run_probe(args):
     # ---- loop A: kernel durations by CUDA events on the launch stream -> `value`, roofline
     probe.SetOption(abi.OPT_EVENT_TIMING, 1)
     step()
-    ev, dev_ms, rd, wr, bar_us = [], [], [], [], []
+    ev, dev_ms, rd, wr, bar_us, ker_ms = [], [], [], [], [], []
     barrier()
     for _ in range(args.steps):
         step()
@@ -344,6 +344,7 @@ def run_probe(args):
         rd.append(out.min_gbps_read)
         wr.append(out.min_gbps_write)
         bar_us.append(out.barrier_us[0])
+        ker_ms.append(out.kernel_ms[0])
     barrier()
     probe.SetOption(abi.OPT_EVENT_TIMING, 0)
 
@@ -369,6 +370,7 @@ def run_probe(args):
     device_ms = max_over_ranks(statistics.mean(dev_ms))
     e2e_ms = max_over_ranks(statistics.mean(host_ms))
     barrier_us = max_over_ranks(statistics.median(bar_us))
+    kernel_ms = max_over_ranks(statistics.mean(ker_ms))
 
     # per-pair GB/s over the whole domain: the last timed step's rows, completed across ranks
     rc = abi.load_library().cdprobe_gather(probe._h, ctypes.byref(out))
@@ -500,9 +502,12 @@ def run_probe(args):
                 "l2": "inputs (1 GiB per pass) exceed the 126 MB L2; no explicit flush",
                 "handle_type": int(info.handle_type),
             },
-            "device_ms_globaltimer": device_ms, "barrier_us": barrier_us,
+            "device_ms_globaltimer": device_ms, "kernel_ms_globaltimer": kernel_ms, "barrier_us": barrier_us,
+            "time_breakdown_note": "value (CUDA events around the launch) >= kernel_ms (CTA 0 entry -> result row published) "
+                                   ">= device_ms (first barrier release -> last phase done); the differences are launch/"
+                                   "completion latency and the residency barrier + row output",
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 2768,
-                    "d2h_bytes_per_step": 32 + 120 * int(res.phases),
+                    "d2h_bytes_per_step": 48 + 120 * int(res.phases),
                     "note": "cdprobe_run from a host thread: kernel parameters (2768 B) in, result row "
                             "(pinned host memory written by the kernel) out; the probe's inputs are "
                             "generated on the device by design"},
@@ -641,7 +646,7 @@ def run_storm(args, pkg, probe, grp, info, n, rank, local, daemon_cost, conf):
                            "bytes_per_pair": res.bytes_per_pair, "mode": "sliced",
                            "parallelism": f"{n} ranks, one process per GPU, no data-path collective"},
                 "e2e": {"value": stats["cycle_ms_p50"], "unit": "ms", "h2d_bytes_per_step": 2768,
-                        "d2h_bytes_per_step": 32 + 120 * int(res.phases),
+                        "d2h_bytes_per_step": 48 + 120 * int(res.phases),
                         "note": "one reconcile cycle through the public ABI: cdprobe_remap_peer + cdprobe_run (p50)"},
                 "gpu_launches": cycles * n, "storm": stats, "parity": parity, "daemon_cost": daemon_cost,
                 "reachability_all_ones": all(all(c == 1 for c in row) for row in res.reach), "verdict": bool(res.verdict),

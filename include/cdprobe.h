@@ -149,6 +149,9 @@ typedef struct {
   float min_gbps_write;
   float gate_gbps_read;                 /* the GB/s threshold this run's verdict applied to reads (0: bandwidth not judged) */
   float gate_gbps_write;
+  double kernel_ms[CDPROBE_MAX_GPUS];   /* per local rank: CTA 0 entering the kernel -> result row published (%globaltimer);
+                                           event_ms - kernel_ms = launch and completion latency outside the kernel,
+                                           kernel_ms - device_ms = residency barrier before the first phase + row output */
   uint32_t unreachable_pairs;           /* filled off-diagonal cells with reach_read & reach_write == 0 (MIG-excluded cells not counted) */
   uint32_t slow_pairs;                  /* filled off-diagonal cells that are reachable but under the gate */
 } cdprobe_result_t;

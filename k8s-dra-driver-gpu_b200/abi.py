@@ -86,6 +86,7 @@ class ResultT(C.Structure):
         ("min_gbps_write", C.c_float),
         ("gate_gbps_read", C.c_float),
         ("gate_gbps_write", C.c_float),
+        ("kernel_ms", C.c_double * MAX_GPUS),
         ("unreachable_pairs", C.c_uint32),
         ("slow_pairs", C.c_uint32),
     ]

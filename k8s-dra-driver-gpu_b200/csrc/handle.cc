@@ -680,6 +680,7 @@ static void assemble(const cdprobe* h, cdprobe_result_t* out) {
     }
     if (row->aborted) out->aborted = 1;
     out->device_ms[li] = row->t_last > row->t_first ? (double)(row->t_last - row->t_first) / 1e6 : 0.0;
+    out->kernel_ms[li] = row->t_exit > row->t_enter ? (double)(row->t_exit - row->t_enter) / 1e6 : 0.0;
     double bar_ns = 0.0;
     bool slow[kMaxRanks] = {};
     for (uint32_t p = 0; p < L.n_phases; ++p) {
@@ -815,6 +816,7 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
       L.row->aborted = h->solo_rank ? 0u : 1u;
       L.row->n_phases = L.n_phases;
       L.row->t_first = L.row->t_last = 0;
+      L.row->t_enter = L.row->t_exit = 0;
       L.row->done = h->launch_seq;
       continue;
     }

@@ -552,7 +552,11 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
   c.stage_smem = smem_u32(smem) + c.warp * kStages * kUnitBytes;
   c.bar_smem = smem_u32(bars) + c.warp * kStages * 8u;
   c.parity_bits = 0u;
-  if (threadIdx.x == 0) s_deadline = gtimer() + P.timeout_ns;
+  __shared__ uint64_t s_enter;
+  if (threadIdx.x == 0) {
+    s_enter = gtimer();
+    s_deadline = s_enter + P.timeout_ns;
+  }
   if (c.lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(c.bar_smem + 8u * s, 1u);
@@ -682,6 +686,8 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
       row->t_last = *reinterpret_cast<volatile uint64_t*>(&ctrl->t_arr[P.n_phases]);
       row->aborted = ab ? 1u : 0u;
       row->n_phases = P.n_phases;
+      row->t_enter = s_enter;
+      row->t_exit = gtimer();
       __threadfence_system();
       st_release_sys(const_cast<uint64_t*>(&row->done), P.run_seq);
     }

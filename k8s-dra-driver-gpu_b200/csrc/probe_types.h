@@ -102,6 +102,7 @@ struct ResultRow {      // pinned host memory, written by CTA 0 at the end of a 
   uint64_t t_first, t_last;
   uint32_t aborted, n_phases;
   PhaseOut ph[kMaxPhases];
+  uint64_t t_enter, t_exit;  // %globaltimer when CTA 0 entered the kernel / just before it published the row
 };
 
 struct ProbeParams {
@@ -119,7 +120,8 @@ struct ProbeParams {
   Phase phase[kMaxPhases];
 };
 static_assert(sizeof(ProbeParams) == 2768, "kernel parameter bytes (bench.py reports them as h2d bytes per step)");
-static_assert(sizeof(PhaseOut) == 120 && offsetof(ResultRow, ph) == 32, "result row bytes (bench.py: d2h per step)");
+static_assert(sizeof(PhaseOut) == 120 && offsetof(ResultRow, ph) == 32 && sizeof(ResultRow) == 32 + 120 * kMaxPhases + 16,
+              "result row bytes (bench.py: d2h per step = 48 + 120 x phases)");
 
 // ---- integer definitions shared with the oracle (oracle/pattern.c restates them) ----
 CDP_HD inline uint64_t splitmix64(uint64_t x) {

@@ -105,6 +105,7 @@ class Result:
     gate_gbps_write: float = 0.0
     unreachable_pairs: int = 0
     slow_pairs: int = 0
+    kernel_ms: List[float] = dataclasses.field(default_factory=list)
     raw: abi.ResultT = dataclasses.field(repr=False, default=None)
 
     @property
@@ -149,6 +150,7 @@ class Result:
             gate_gbps_write=r.gate_gbps_write,
             unreachable_pairs=r.unreachable_pairs,
             slow_pairs=r.slow_pairs,
+            kernel_ms=list(r.kernel_ms)[:n],
             raw=r,
         )
 

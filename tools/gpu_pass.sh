@@ -9,7 +9,7 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 O=gpurun_out/${TAG}
 if [ -z "$SKIP_TESTS" ]; then
-  timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 --timeout 400 -p no:cacheprovider > ${O}_pytest_n$N.log 2>&1
+  timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 --timeout 400 -p no:cacheprovider ${TESTS_K:+-k "$TESTS_K"} > ${O}_pytest_n$N.log 2>&1
   echo "pytest exit=$?"; tail -12 ${O}_pytest_n$N.log
 fi
 if [ "$N" -gt 1 ]; then
