@@ -39,6 +39,12 @@ NVLINK_PEAK_GBPS = 900.0        # nominal per direction per GPU (BASELINE.md §2
 NVLINK_GUIDE_CE_GBPS = 770.0    # the profiling guide's peer-copy figure; the line carries the SAME-BOX copy-engine
                                 # numbers measured next to the probe (roofline.peak_measured_ce_{uni,bidi})
 HBM_FALLBACK_GBPS = 6650.0
+# Bytes on the NVLink wire per payload byte of SM-issued traffic, from ncu's nvltx/nvlrx counters on the solo probe
+# kernel (profiles/r02_ncu_nvlink_{read,write}.csv; 1 GiB of payload each): a read costs 1.125 B of response in the
+# payload direction (32 B per 256-B response) and 0.1875 B of request in the opposite one (48 B per 256 B); a write
+# costs 1.1875 B in the payload direction and ~0.003 B of acknowledgement back.
+WIRE = {"read_rx": 1207959648 / 1073741888, "read_tx_req": 201326656 / 1073741888,
+        "write_tx": 1275068544 / 1073741888, "write_rx_ack": 3453312 / 1073741888}
 
 
 def measured_peaks():
@@ -480,6 +486,17 @@ def run_probe(args):
                     "frac_read_of_ce_bidi": min(pairs_r) / ce["bidi_push_min"],
                     "frac_write_of_ce_bidi": min(pairs_w) / ce["bidi_push_min"],
                     "ce": ce,
+                    # wire-level view: with both directions loaded a port's direction carries, per payload byte of its own
+                    # op, the payload + protocol of that op plus the requests/acks of the opposite direction's op
+                    "wire_bytes_per_payload_byte": WIRE,
+                    "wire_gbps_read_phase": min(pairs_r) * (WIRE["read_rx"] + WIRE["read_tx_req"]),
+                    "wire_gbps_write_phase": min(pairs_w) * (WIRE["write_tx"] + WIRE["write_rx_ack"]),
+                    "frac_wire_read_phase_of_900": min(pairs_r) * (WIRE["read_rx"] + WIRE["read_tx_req"]) / NVLINK_PEAK_GBPS,
+                    "frac_wire_write_phase_of_900": min(pairs_w) * (WIRE["write_tx"] + WIRE["write_rx_ack"]) / NVLINK_PEAK_GBPS,
+                    "payload_ceiling_read_bidi": NVLINK_PEAK_GBPS / (WIRE["read_rx"] + WIRE["read_tx_req"]),
+                    "payload_ceiling_write_bidi": NVLINK_PEAK_GBPS / (WIRE["write_tx"] + WIRE["write_rx_ack"]),
+                    "wire_source": "profiles/r02_ncu_nvlink_read.csv, profiles/r02_ncu_nvlink_write.csv (ncu nvltx__/nvlrx__ "
+                                   "bytes of the solo probe kernel)",
                     "kernel": "cdprobe_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                     "nvlink_bytes_per_launch_per_direction": a_gpu,
                     "aggregate_link_gbps_per_gpu": link_bytes / (value * 1e-3) / 1e9,
