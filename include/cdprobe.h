@@ -80,6 +80,9 @@ extern "C" {
 #define CDPROBE_FLAG_ALL_RANK_BARRIERS 0x400u /* every tournament phase closes with an all-rank flag exchange (round-1
                                               behaviour); default: only the ranks whose traffic shares an NVLink
                                               port with this rank's in the two phases either side of the barrier */
+#define CDPROBE_FLAG_PAIR_BARRIERS 0x800u  /* keep the pair's flag exchange between the write and the read phase of a round
+                                              (default: no wait there — the rank only signals its partner and the
+                                              verify job waits for that signal itself) */
 #define CDPROBE_FLAG_UNIDIRECTIONAL 0x80u  /* each round in two halves: one rank of a pair issues at a time, so a
                                               port carries payload one way only (per-link figure; 2x the phases) */
 
@@ -200,6 +203,7 @@ typedef struct {
   int8_t peer0[CDPROBE_MAX_PHASES], peer1[CDPROBE_MAX_PHASES];
   uint8_t sync_all[CDPROBE_MAX_PHASES];                          /* closing barrier spans all ranks */
   uint16_t sync_mask[CDPROBE_MAX_PHASES];                        /* ranks of the closing barrier's flag exchange */
+  uint16_t post_mask[CDPROBE_MAX_PHASES];                        /* ranks only signalled at the closing barrier (no wait) */
   uint64_t t_start[CDPROBE_MAX_PHASES];                          /* opening barrier released */
   uint64_t t_end0[CDPROBE_MAX_PHASES], t_end1[CDPROBE_MAX_PHASES]; /* last CTA of job 0 / job 1 done */
   uint64_t t_arrive[CDPROBE_MAX_PHASES];                         /* every local CTA reached the closing barrier */
@@ -218,6 +222,9 @@ typedef struct {
   uint16_t cta0[2][CDPROBE_MAX_PHASES], nctas[2][CDPROBE_MAX_PHASES];
   uint8_t sync_all[CDPROBE_MAX_PHASES];            /* closing barrier spans all ranks */
   uint16_t sync_mask[CDPROBE_MAX_PHASES];          /* ranks this rank exchanges flags with when the phase closes */
+  uint16_t post_mask[CDPROBE_MAX_PHASES];          /* ranks it only signals then (no wait) */
+  uint8_t wait_barrier[2][CDPROBE_MAX_PHASES];     /* [job][phase] verify jobs: 1-based barrier index whose signal from
+                                                      `writer` the job waits for before reading the slot (0 = none) */
 } cdprobe_schedule_t;
 
 /* Node topology as NVML reports it (no CUDA; internal/common topology enumeration). */
@@ -282,6 +289,7 @@ CDPROBE_API int cdprobe_trace(cdprobe_t* h, uint32_t local, cdprobe_trace_t* out
                                         cross-GPU barrier, nobody verifies its writes (reach_write stays 0).  A single
                                         self-contained kernel is what `ncu` can replay: NVLink byte counters per launch. */
 #define CDPROBE_OPT_ALL_RANK_BARRIERS 15u /* value 0/1: see CDPROBE_FLAG_ALL_RANK_BARRIERS */
+#define CDPROBE_OPT_PAIR_BARRIERS 16u     /* value 0/1: see CDPROBE_FLAG_PAIR_BARRIERS */
 CDPROBE_API int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value);
 /* Copy-engine reference on the probe's own buffers (the same-box ceiling the roofline is quoted against; not part
  * of a probe): copy k moves `bytes` (capped at the source / landing size) `reps` times back to back between local

@@ -25,11 +25,13 @@ FLAG_UNIDIRECTIONAL = 0x80
 FLAG_SERIAL_VERIFY = 0x100
 FLAG_SIMULATE_MIG = 0x200
 FLAG_ALL_RANK_BARRIERS = 0x400
+FLAG_PAIR_BARRIERS = 0x800
 
 OPT_EVENT_TIMING, OPT_CTAS, OPT_PATH, OPT_TIMEOUT_MS, OPT_OVERLAP_VERIFY, OPT_VERIFY_CTAS = 1, 2, 3, 4, 5, 6
 OPT_UNIDIRECTIONAL = 7
 OPT_WARMUP, OPT_WARMUP_BYTES, OPT_DEBUG_SKIP_RANK = 8, 9, 10
 OPT_CTAS_RANK, OPT_MIN_FRACTION_PPM, OPT_LINK_PEAK_MBPS, OPT_SOLO_RANK, OPT_ALL_RANK_BARRIERS = 11, 12, 13, 14, 15
+OPT_PAIR_BARRIERS = 16
 
 _N2 = MAX_GPUS * MAX_GPUS
 
@@ -141,6 +143,7 @@ class TraceT(C.Structure):
         ("peer1", C.c_int8 * MAX_PHASES),
         ("sync_all", C.c_uint8 * MAX_PHASES),
         ("sync_mask", C.c_uint16 * MAX_PHASES),
+        ("post_mask", C.c_uint16 * MAX_PHASES),
         ("t_start", C.c_uint64 * MAX_PHASES),
         ("t_end0", C.c_uint64 * MAX_PHASES),
         ("t_end1", C.c_uint64 * MAX_PHASES),
@@ -176,6 +179,8 @@ class ScheduleT(C.Structure):
         ("nctas", (C.c_uint16 * MAX_PHASES) * 2),
         ("sync_all", C.c_uint8 * MAX_PHASES),
         ("sync_mask", C.c_uint16 * MAX_PHASES),
+        ("post_mask", C.c_uint16 * MAX_PHASES),
+        ("wait_barrier", (C.c_uint8 * MAX_PHASES) * 2),
     ]
 
 

@@ -336,6 +336,7 @@ static int fill_and_publish(cdprobe* h) {
       ph[s].job[0].cta0 = 0;
       ph[s].job[0].nctas = (uint16_t)L.ctas;
       ph[s].sync_mask = 0;
+      ph[s].post_mask = 0;
     }
     ProbeParams P;
     fill_params(h, li, ph, pl.n_slices, 0u, &P);
@@ -826,6 +827,7 @@ int cdprobe_run(cdprobe_t* h, cdprobe_result_t* out) {
       for (uint32_t p = 0; p < L.n_phases; ++p) {
         solo[p] = L.phases[p];
         solo[p].sync_mask = 0;
+        solo[p].post_mask = 0;
         for (int jb = 0; jb < 2; ++jb)
           if (solo[p].job[jb].kind == cdp::kJobVerify) solo[p].job[jb].kind = cdp::kJobNone;
       }
@@ -969,6 +971,7 @@ int cdprobe_trace(cdprobe_t* h, uint32_t local, cdprobe_trace_t* out) {
     out->peer0[p] = L.phases[p].job[0].peer;
     out->peer1[p] = L.phases[p].job[1].peer;
     out->sync_mask[p] = (uint16_t)(L.phases[p].sync_mask & L.peer_mask);
+    out->post_mask[p] = (uint16_t)(L.phases[p].post_mask & L.peer_mask);
     out->sync_all[p] = (uint8_t)(L.peer_mask != 0 && (L.phases[p].sync_mask & L.peer_mask) == L.peer_mask);
     out->t_start[p] = rel(o.t_start);
     out->t_end0[p] = rel(o.t_end[0]);
@@ -1026,6 +1029,17 @@ int cdprobe_set_option(cdprobe_t* h, uint32_t option, uint64_t value) {
     {
       const uint32_t old = h->cfg.flags;
       h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_ALL_RANK_BARRIERS) | (value ? CDPROBE_FLAG_ALL_RANK_BARRIERS : 0u);
+      const int rc = cdp::rebuild_all(h);
+      if (rc != CDPROBE_OK) {
+        h->cfg.flags = old;
+        cdp::rebuild_all(h);
+      }
+      return rc;
+    }
+    case CDPROBE_OPT_PAIR_BARRIERS:
+    {
+      const uint32_t old = h->cfg.flags;
+      h->cfg.flags = (h->cfg.flags & ~CDPROBE_FLAG_PAIR_BARRIERS) | (value ? CDPROBE_FLAG_PAIR_BARRIERS : 0u);
       const int rc = cdp::rebuild_all(h);
       if (rc != CDPROBE_OK) {
         h->cfg.flags = old;

@@ -444,20 +444,34 @@ __device__ void job_write_stg256(Ctx& c, uint8_t* base, uint64_t bytes, uint32_t
 }
 
 // ---------------------------------------------------------- K3: barrier ----
-// Leader-only work done when every local CTA has finished phase `ph`.
-__device__ void phase_epilogue(const ProbeParams& P, Ctrl* ctrl, int ph, bool is_aborted) {
-  if (is_aborted) return;
+// Leader-only publications once every local CTA has finished a phase.
+//  * a write job: (S, X, run_seq) of what was stored, into the owner's Ctrl, so that the owner can verify the
+//    landing slot — must be visible before the flag that tells the owner "phase done";
+//  * verify jobs: the verdict goes back to the writer.  Writers read it only when they assemble their result row,
+//    after the last barrier of the run, so ALL verdicts are published by the last barrier's leader in one go (one
+//    thread, one fence: no cross-thread ordering argument needed).
+__device__ bool publish_writes(const ProbeParams& P, Ctrl* ctrl, int ph) {
+  bool any = false;
 #pragma unroll
   for (int jb = 0; jb < 2; ++jb) {
     const Job job = P.phase[ph].job[jb];
+    if (job.kind != kJobWrite) continue;
     const volatile Acc* acc = &ctrl->acc[ph][jb];
-    if (job.kind == kJobWrite) {
-      // publish what was written so the owner of the landing slot can verify it
-      Ctrl* pc = reinterpret_cast<Ctrl*>(P.base_peer[job.peer]);
-      st_relaxed_sys(&pc->wr[job.slot].sum, acc->sum);
-      st_relaxed_sys(&pc->wr[job.slot].xr, acc->xr);
-      st_relaxed_sys(&pc->wr[job.slot].seq, P.run_seq);
-    } else if (job.kind == kJobVerify) {
+    Ctrl* pc = reinterpret_cast<Ctrl*>(P.base_peer[job.peer]);
+    st_relaxed_sys(&pc->wr[job.slot].sum, acc->sum);
+    st_relaxed_sys(&pc->wr[job.slot].xr, acc->xr);
+    st_relaxed_sys(&pc->wr[job.slot].seq, P.run_seq);
+    any = true;
+  }
+  return any;
+}
+__device__ void publish_verdicts(const ProbeParams& P, Ctrl* ctrl) {
+  for (uint32_t ph = 0; ph < P.n_phases; ++ph) {
+#pragma unroll
+    for (int jb = 0; jb < 2; ++jb) {
+      const Job job = P.phase[ph].job[jb];
+      if (job.kind != kJobVerify) continue;
+      const volatile Acc* acc = &ctrl->acc[ph][jb];
       const uint64_t wsum = ld_relaxed_sys(&ctrl->wr[job.slot].sum);
       const uint64_t wxr = ld_relaxed_sys(&ctrl->wr[job.slot].xr);
       const uint64_t wseq = ld_relaxed_sys(&ctrl->wr[job.slot].seq);
@@ -469,11 +483,23 @@ __device__ void phase_epilogue(const ProbeParams& P, Ctrl* ctrl, int ph, bool is
   }
 }
 
-// Barrier b: b == 0 opens the run, barrier b >= 1 closes phase b - 1.  `mask` = the ranks whose
-// traffic touches the same NVLink ports as this rank's in the phases either side of the barrier
-// (schedule.cc: current partner, next partner and their partners; every rank at open and close).
-// The relation is symmetric, so every rank this one waits for also signals it.
-__device__ void barrier(const ProbeParams& P, Ctx& c, int b, uint32_t mask) {
+__device__ __forceinline__ void signal_ranks(const ProbeParams& P, uint32_t mask, uint64_t target) {
+  for (uint32_t j = 0; j < P.n_ranks; ++j) {
+    if (j == P.rank || !((mask >> j) & 1u)) continue;
+    st_relaxed_sys(&reinterpret_cast<Ctrl*>(P.base_peer[j])->flags[P.rank].v, target);
+  }
+}
+
+// Barrier b: b == 0 opens the run, barrier b >= 1 closes phase b - 1.
+//   sync = ranks to exchange flags with (signal, then wait): the ranks whose traffic touches the same NVLink ports
+//          as this rank's in the phases either side of the barrier (schedule.cc: current partner, next partner and
+//          their partners; every rank at open and close).  Symmetric: whoever is waited for also signals.
+//   post = ranks that are only signalled, AFTER this rank's own CTAs have been released: the write -> read step
+//          inside a round — nobody waits there; the verify job that needs the partner's data polls for it itself.
+// A system-scope fence precedes the flag stores only when this rank published something the receiver acts on at
+// this barrier (write checksums; the verdicts at the last barrier): reads leave nothing in flight, and each CTA
+// already fenced its own remote stores before it arrived.
+__device__ void barrier(const ProbeParams& P, Ctx& c, int b, uint32_t sync, uint32_t post, bool last) {
   __syncthreads();
   if (threadIdx.x == 0) {
     Ctrl* ctrl = c.ctrl;
@@ -489,18 +515,21 @@ __device__ void barrier(const ProbeParams& P, Ctx& c, int b, uint32_t mask) {
         *reinterpret_cast<volatile unsigned int*>(&ctrl->grid_arrive) = 0u;
         __threadfence();
         const uint64_t t_arr = gtimer();
-        if (b >= 1) phase_epilogue(P, ctrl, b - 1, false);
-        bool timed_out = false;
-        if (mask) {
-          // One system-scope fence, then relaxed flag stores that pipeline over NVLink.  (A
-          // st.release.sys per peer serialises a round trip per store: ~2 us x 7 peers per barrier.)
-          __threadfence_system();
-          for (uint32_t j = 0; j < P.n_ranks; ++j) {
-            if (j == P.rank || !((mask >> j) & 1u)) continue;
-            st_relaxed_sys(&reinterpret_cast<Ctrl*>(P.base_peer[j])->flags[P.rank].v, target);
+        bool published = false, wrote_done = false;
+        if (sync) {
+          if (b >= 1) {
+            published = publish_writes(P, ctrl, b - 1);
+            wrote_done = true;
           }
+          if (last) {
+            publish_verdicts(P, ctrl);
+            published = true;
+          }
+          if (published) __threadfence_system();  // one fence, then relaxed flag stores that pipeline over NVLink
+          signal_ranks(P, sync, target);
+          bool timed_out = false;
           for (uint32_t j = 0; j < P.n_ranks && !timed_out; ++j) {
-            if (j == P.rank || !((mask >> j) & 1u)) continue;
+            if (j == P.rank || !((sync >> j) & 1u)) continue;
             uint32_t spins = 0;
             while (ld_acquire_sys(&ctrl->flags[j].v) < target) {
               if ((++spins & 63u) == 0u && check_abort(c)) {
@@ -509,11 +538,22 @@ __device__ void barrier(const ProbeParams& P, Ctx& c, int b, uint32_t mask) {
               }
             }
           }
+        } else if (last) {
+          publish_verdicts(P, ctrl);  // single-rank domains: the verdict word is local
+          __threadfence_system();
         }
         const uint64_t t_rel = gtimer();
         ctrl->t_arr[b] = t_arr;
         ctrl->t_rel[b] = t_rel;
         st_release_gpu(&ctrl->grid_release, target);
+        // off the critical path: the local CTAs are already running the next phase
+        if (post && !aborted(c)) {
+          if (b >= 1 && !wrote_done) publish_writes(P, ctrl, b - 1);
+          __threadfence_system();
+          signal_ranks(P, post, target);
+        } else if (b >= 1 && !wrote_done && !aborted(c)) {
+          if (publish_writes(P, ctrl, b - 1)) __threadfence_system();  // loop-back write: the owner is this GPU
+        }
       } else {
         uint32_t spins = 0;
         while (ld_acquire_gpu(&ctrl->grid_release) < target) {
@@ -565,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
   __syncthreads();
   c.deadline = s_deadline;
 
-  barrier(P, c, 0, P.peer_mask);
+  barrier(P, c, 0, P.peer_mask, 0u, false);
 
   for (uint32_t ph = 0; ph < P.n_phases; ++ph) {
     const Phase& phd = P.phase[ph];
@@ -594,10 +634,26 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
           else if (P.use_ldst == 1u) job_read_ldg(c, src, P.bpp, gwarp, nwarps, a);
           else job_read_tma(c, src, P.bpp, gwarp, nwarps, a);
         } else if (job.kind == kJobVerify) {
-          const uint8_t* src = pb + P.land_off + (uint64_t)job.slot * P.bpp;
-          if (P.use_ldst == 2u) job_read_ldg256(c, src, P.bpp, gwarp, nwarps, a);
-          else if (P.use_ldst == 1u) job_read_ldg(c, src, P.bpp, gwarp, nwarps, a);
-          else job_read_tma(c, src, P.bpp, gwarp, nwarps, a);
+          // the slot's writer signals when its write phase is over (and its checksums are published); where the
+          // schedule put no wait between that phase and this one (post_mask), this job does the waiting
+          bool go = true;
+          if (job.salt != 0 && job.writer != P.rank && P.base_peer[job.writer] != nullptr) {
+            if (threadIdx.x == 0) {
+              const uint64_t need = P.seq_base + job.salt + 1ull;
+              uint32_t spins = 0;
+              while (ld_acquire_sys(&c.ctrl->flags[job.writer].v) < need) {
+                if ((++spins & 63u) == 0u && check_abort(c)) break;
+              }
+            }
+            __syncthreads();
+            go = !aborted(c);
+          }
+          if (go) {
+            const uint8_t* src = pb + P.land_off + (uint64_t)job.slot * P.bpp;
+            if (P.use_ldst == 2u) job_read_ldg256(c, src, P.bpp, gwarp, nwarps, a);
+            else if (P.use_ldst == 1u) job_read_ldg(c, src, P.bpp, gwarp, nwarps, a);
+            else job_read_tma(c, src, P.bpp, gwarp, nwarps, a);
+          }
         } else {
           uint8_t* dst = pb + P.land_off + (uint64_t)job.slot * P.bpp;
           if (P.use_ldst == 2u) job_write_stg256(c, dst, P.bpp, gwarp, nwarps, job.salt, a);
@@ -627,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
         atomicMax(&acc->t_end, (unsigned long long)gtimer());
       }
     }
-    barrier(P, c, (int)ph + 1, phd.sync_mask & P.peer_mask);
+    barrier(P, c, (int)ph + 1, phd.sync_mask & P.peer_mask, phd.post_mask & P.peer_mask, ph + 1 == P.n_phases);
   }
 
   // ---- output: CTA 0 writes the result row into pinned host memory ----------

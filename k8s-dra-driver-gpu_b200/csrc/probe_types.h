@@ -78,13 +78,15 @@ struct Job {            // 16 bytes
   uint8_t writer;       // verify: rank that wrote the slot
   uint16_t cta0;        // first CTA of the job
   uint16_t nctas;       // CTAs of the job
-  uint64_t salt;        // write: pattern salt; warm: bytes to stream (0 = skip)
+  uint64_t salt;        // write: pattern salt; warm: bytes to stream (0 = skip); verify: index b >= 1 of the barrier
+                        // whose signal from `writer` the job waits for before it reads the slot (0 = none)
 };
 
 struct Phase {          // 40 bytes
   Job job[2];
   uint32_t sync_mask;   // ranks this GPU exchanges barrier flags with when the phase closes (0: this GPU only)
-  uint32_t pad;
+  uint32_t post_mask;   // ranks it only SIGNALS then (after releasing its own CTAs): a write -> read step inside a round,
+                        // where the next phase needs the partner's data (the verify job waits for it) but not its ports
 };
 
 struct PhaseOut {

@@ -206,7 +206,7 @@ class Probe:
             _raise(self._lib, rc, "cdprobe_trace")
         names = {0: "-", 1: "read", 2: "write", 3: "verify", 4: "warm"}
         return [{"job0": names[t.kind0[p]], "peer0": t.peer0[p], "job1": names[t.kind1[p]], "peer1": t.peer1[p],
-                 "sync_all": int(t.sync_all[p]), "sync_mask": int(t.sync_mask[p]), "t_start": t.t_start[p], "t_end0": t.t_end0[p], "t_end1": t.t_end1[p],
+                 "sync_all": int(t.sync_all[p]), "sync_mask": int(t.sync_mask[p]), "post_mask": int(t.post_mask[p]), "t_start": t.t_start[p], "t_end0": t.t_end0[p], "t_end1": t.t_end1[p],
                  "t_arrive": t.t_arrive[p]} for p in range(t.n_phases)]
 
     def SetOption(self, option: int, value: int) -> None:

@@ -487,22 +487,29 @@ def test_throttled_issuer_fails_only_its_own_pairs(pkg, oracle):
 
 
 @pytest.mark.parametrize("n", [2, 4, 5])
-def test_neighbourhood_and_all_rank_barriers_agree(pkg, oracle, n):
-    """Default (neighbourhood) barriers and the round-1 all-rank exchange give the same bits and checksums."""
+def test_barrier_schedules_agree(pkg, oracle, n):
+    """The default schedule (neighbourhood exchanges between rounds, NO wait between the write and the read phase of
+    a round — the verify job polls for its writer's signal), the same with the pair exchange kept, and round 1's
+    all-rank exchange everywhere: same bits, same checksums, run after run."""
     nbytes = 2 << 20
     with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME, ctas=8, timeout_ms=20000)) as p:
-        for all_rank in (0, 1, 0):
+        for all_rank, pair in ((0, 0), (0, 1), (1, 0), (0, 0)):
             p.SetOption(pkg.abi.OPT_ALL_RANK_BARRIERS, all_rank)
+            p.SetOption(pkg.abi.OPT_PAIR_BARRIERS, pair)
             for _ in range(3):
                 r = p.Run()
                 check_full_parity(pkg, oracle, r, n, nbytes, pkg.abi.MODE_SLICED, 3)
                 assert r.reach == [[1] * n for _ in range(n)] and not r.aborted
             tr = p.Trace(0)
-            if n > 2:
-                # inside a round (write -> read of the same pair) the default exchange is the pair alone
-                inner = [t for t, nxt in zip(tr, tr[1:]) if t["job0"] == "write" and nxt["job0"] == "read" and t["peer0"] == nxt["peer0"]]
-                assert inner and all(bool(t["sync_all"]) == bool(all_rank) for t in inner)
-                assert all_rank or all(bin(t["sync_mask"]).count("1") == 1 for t in inner)
+            inner = [t for t, nxt in zip(tr, tr[1:]) if t["job0"] == "write" and nxt["job0"] == "read" and t["peer0"] == nxt["peer0"]]
+            assert inner
+            for t in inner:
+                if all_rank:
+                    assert t["sync_all"] == 1 and t["post_mask"] == 0
+                elif pair:
+                    assert bin(t["sync_mask"]).count("1") == 1 and t["post_mask"] == 0
+                else:
+                    assert t["sync_mask"] == 0 and bin(t["post_mask"]).count("1") == 1
             assert tr[-1]["sync_all"] == 1
 
 

@@ -18,7 +18,7 @@ import itertools
 import pytest
 
 NONE, READ, WRITE, VERIFY, WARM = 0, 1, 2, 3, 4
-UNI, SERIAL, DIAG, ALLRANK = 0x80, 0x100, 0x04, 0x400
+UNI, SERIAL, DIAG, ALLRANK, PAIRBAR = 0x80, 0x100, 0x04, 0x400, 0x800
 
 
 def schedule(pkg, n, rank, mode=1, ops=3, flags=0, ctas=148, vctas=32, nbytes=1 << 30):
@@ -41,7 +41,7 @@ def slot_of(i, j):
     return i if i < j else i - 1
 
 
-CASES = [dict(flags=f, ops=o, ctas=c) for f in (0, UNI, SERIAL, UNI | SERIAL, DIAG, UNI | DIAG, ALLRANK, ALLRANK | UNI)
+CASES = [dict(flags=f, ops=o, ctas=c) for f in (0, UNI, SERIAL, UNI | SERIAL, DIAG, UNI | DIAG, ALLRANK, ALLRANK | UNI, PAIRBAR)
          for o in (1, 2, 3) for c in (148, 8, 1)]
 
 
@@ -62,10 +62,14 @@ def test_schedule_invariants(pkg, n, case):
     for r, t in enumerate(tabs):
         assert t.n_phases == np_ and t.peer_mask == everyone[r]
         for ph in range(np_):
-            assert t.sync_mask[ph] & ~everyone[r] == 0
+            assert t.sync_mask[ph] & ~everyone[r] == 0 and t.post_mask[ph] & ~everyone[r] == 0
+            assert t.sync_mask[ph] & t.post_mask[ph] == 0
             assert t.sync_all[ph] == (1 if n > 1 and t.sync_mask[ph] == everyone[r] else 0)
             for j in range(n):
                 assert bool(t.sync_mask[ph] >> j & 1) == bool(tabs[j].sync_mask[ph] >> r & 1), "asymmetric barrier"
+                assert bool(t.post_mask[ph] >> j & 1) == bool(tabs[j].post_mask[ph] >> r & 1), "asymmetric post"
+            if flags & (UNI | ALLRANK | PAIRBAR):
+                assert t.post_mask[ph] == 0  # the no-wait step exists only in the default bidirectional schedule
     if np_ and n > 1:
         assert all(t.sync_all[np_ - 1] == 1 for t in tabs)
     # ports[ph][r] = the ranks whose NVLink ports rank r's phase-ph transfer loads (both ends of its pair,
@@ -81,7 +85,13 @@ def test_schedule_invariants(pkg, n, case):
         for x in range(n):
             for y in range(n):
                 if x != y and ports[ph + 1][x] & ports[ph][y]:
-                    assert tabs[x].sync_mask[ph] >> y & 1, f"phase {ph}: rank {x} may start while {y} still uses its port"
+                    if tabs[x].sync_mask[ph] >> y & 1:
+                        continue
+                    # the one exception: write -> read inside a round.  The ports are the PAIR's own on both sides of
+                    # the barrier; y is only signalled (post), and whatever needs y's data waits for that signal itself
+                    assert tabs[x].post_mask[ph] >> y & 1, f"phase {ph}: rank {x} may start while {y} still uses its port"
+                    assert ports[ph][y] == ports[ph + 1][x] == {x, y}
+                    assert tabs[x].kind[0][ph] in (WRITE, NONE) and tabs[x].kind[0][ph + 1] in (READ, NONE)
     reads, writes, verifies = {}, {}, {}
     for ph in range(np_):
         touched_by = {}
@@ -93,7 +103,7 @@ def test_schedule_invariants(pkg, n, case):
                 assert 0 <= p < n
                 assert p not in touched_by, "two ranks hit the same peer in one phase"
                 touched_by[p] = r
-                assert t.sync_mask[ph] >> p & 1  # a pair always closes its transfer together
+                assert (t.sync_mask[ph] | t.post_mask[ph]) >> p & 1  # a pair always tells each other a transfer is over
                 if flags & ALLRANK:
                     assert t.sync_all[ph] == 1  # round-1 behaviour: remote traffic closed by an all-rank barrier
                 # the pairing is the tournament's: p's partner in that round is r
@@ -137,8 +147,15 @@ def test_schedule_invariants(pkg, n, case):
         assert set(verifies) == set(writes)  # every written slot is verified exactly once, by its owner
         for (w, o), (ph, slot) in verifies.items():
             assert ph > writes[(w, o)] or (w == o and ph > writes[(w, o)])
-            if w != o:  # the owner learns of the write (and its published checksum) at the write phase's own barrier
-                assert tabs[o].sync_mask[writes[(w, o)]] >> w & 1
+            if w != o:  # the writer signals the owner (and has published its checksum) at the write phase's own barrier ...
+                wp = writes[(w, o)]
+                assert (tabs[w].sync_mask[wp] | tabs[w].post_mask[wp]) >> o & 1
+                # ... and the verify job waits for exactly that signal before it touches the slot
+                jb = 0 if tabs[o].kind[0][ph] == VERIFY and tabs[o].writer[0][ph] == w else 1
+                assert tabs[o].kind[jb][ph] == VERIFY and tabs[o].wait_barrier[jb][ph] == wp + 1
+            else:
+                jb = 0 if tabs[o].kind[0][ph] == VERIFY and tabs[o].writer[0][ph] == w else 1
+                assert tabs[o].wait_barrier[jb][ph] == 0
             assert slot == (slot_of(w, o) if w != o else n - 1)
     else:
         assert not writes and not verifies
@@ -158,8 +175,11 @@ def test_default_8gpu_table_shape(pkg):
     # pair alone; between rounds at most 4 ranks
     for t in tabs:
         assert [t.sync_all[p] for p in range(15)] == [0] * 14 + [1]
-        assert all(bin(t.sync_mask[p]).count("1") == 1 for p in [0] + list(range(1, 14, 2)))  # warm->W(0), W(r)->R(r)
-        assert all(2 <= bin(t.sync_mask[p]).count("1") <= 4 for p in range(2, 14, 2))          # R(r) -> W(r+1)
+        assert bin(t.sync_mask[0]).count("1") == 1 and t.post_mask[0] == 0                      # warm -> W(0): the pair
+        assert all(t.sync_mask[p] == 0 and bin(t.post_mask[p]).count("1") == 1 for p in range(1, 14, 2))  # W(r) -> R(r): no wait
+        assert all(2 <= bin(t.sync_mask[p]).count("1") <= 4 and t.post_mask[p] == 0 for p in range(2, 14, 2))  # R(r) -> W(r+1)
+    rc, pb = table(pkg, 8, flags=PAIRBAR)
+    assert rc == 0 and all(bin(pb[0].sync_mask[p]).count("1") == 1 and pb[0].post_mask[p] == 0 for p in range(1, 14, 2))
     rc, old = table(pkg, 8, flags=ALLRANK)
     assert rc == 0 and all(old[0].sync_all[p] == 1 for p in range(15))
 

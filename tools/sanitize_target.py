@@ -15,7 +15,7 @@ SEED = o.DEFAULT_SEED
 for path in (0, 1, 2):  # TMA bulk, 128-bit ld/st, 256-bit ld/st
     for n, mode, nbytes, extra in ((1, 1, (1 << 20) + 128 * 5, 0), (2, 0, 1 << 20, 0), (2, 1, (1 << 19) + 128 * 3, 0),
                                    (3, 1, 3 << 18, 0), (4, 1, 1 << 19, 0x80), (4, 1, 1 << 19, 0x20),
-                                   (4, 1, 1 << 19, 0x400), (5, 1, 5 << 17, 0)):  # all-rank barriers; odd domain
+                                   (4, 1, 1 << 19, 0x400), (4, 1, 1 << 19, 0x800), (5, 1, 5 << 17, 0)):  # all-rank / pair barriers; odd domain
         flags = extra | (0x40 | 0x10 if n > 1 else 0)
         with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, mode=mode, flags=flags, ctas=4, timeout_ms=120000)) as p:
             p.SetOption(pkg.abi.OPT_PATH, path)

@@ -24,7 +24,8 @@ ap.add_argument("--overlap", default="0")
 ap.add_argument("--uni", default="0")
 ap.add_argument("--paths", default="0,1")
 ap.add_argument("--vctas", type=int, default=32)
-ap.add_argument("--barriers", default="0", help="0 = neighbourhood (default), 1 = all-rank (round 1)")
+ap.add_argument("--barriers", default="0", help="0 = default (neighbourhood + no wait write->read), 1 = all-rank (round 1), "
+                                              "2 = neighbourhood with the pair exchange kept between write and read")
 args = ap.parse_args()
 
 mode = {"sliced": 1, "full": 2, "reach": 0}[args.mode]
@@ -37,7 +38,8 @@ with pkg.Open(pkg.Config(ordinals=list(range(n)), bytes=args.bytes, mode=mode, t
         p.SetOption(abi.OPT_UNIDIRECTIONAL, uni)
         p.SetOption(abi.OPT_OVERLAP_VERIFY, overlap)
         for allrank in [int(b) for b in args.barriers.split(",")]:
-            p.SetOption(abi.OPT_ALL_RANK_BARRIERS, allrank)
+            p.SetOption(abi.OPT_ALL_RANK_BARRIERS, 1 if allrank == 1 else 0)
+            p.SetOption(abi.OPT_PAIR_BARRIERS, 1 if allrank == 2 else 0)
             for path in [int(x) for x in args.paths.split(",")]:
                 p.SetOption(abi.OPT_PATH, path)
                 for ctas in [int(c) for c in args.ctas.split(",")]:
