@@ -1,4 +1,4 @@
-"""The bench.py JSON contract, checked on the lines recorded on the B200 boxes (profiles/r01_final_*):
+"""The bench.py JSON contract, checked on the lines recorded on the B200 boxes (profiles/r01_final_*, profiles/r02_*):
 every key the driver reads is present with the right type and the numbers are internally consistent.
 (The lines themselves were produced by `bench.py` on GPU; this guards the schema on CPU.)"""
 import json
@@ -64,3 +64,69 @@ def test_reference_arm_line(n):
     ours = load(f"r01_final_bench_n{n}.json")
     if "workload" in j["config"] and "reference_path" in j["config"]:
         assert j["config"]["workload"] == ours["config"]["workload"]  # both arms answer the same question
+
+
+# ---- round 2 lines: parity block, same-box CE ceilings, daemon cost, configs c2 / c3-full / c5 ----------------
+def _common_r02(j, n):
+    for k, t in REQUIRED.items():
+        if k == "roofline" and j["config"].get("config") == "c5":
+            continue
+        assert k in j, k
+        assert isinstance(j[k], t) or (t is float and isinstance(j[k], int)), (k, type(j[k]))
+    assert j["metric"] == "nvlink_probe_ms" and j["unit"] == "ms" and j["higher_is_better"] is False
+    assert j["n_gpus"] == n and j["vs_baseline"] is None and j["scaling"] == "weak" and j["warmup"] >= 3
+    p = j["parity"]
+    assert p["cells"] == (n * (n - 1) if n > 1 else 1) and p["checksum_ok"] is True and p["reach_vs_nvml_ok"] is True
+    assert p["checksum_mismatches"] == [] and p["nvml_gpus_polled"] >= n
+    d = j["daemon_cost"]
+    assert d["cold_first_verdict_ms"] >= d["open_ms"] > 0 and d["first_run_ms"] > 0
+    assert j["reachability_all_ones"] is True and j["verdict"] is True
+    c = j["clocks"]
+    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+@pytest.mark.parametrize("n", [1, 2, 8])
+def test_r02_headline_line(n):
+    j = load(f"r02_bench_n{n}.json")
+    _common_r02(j, n)
+    assert j["gpu_launches"] == j["steps"] * n
+    assert j["value"] >= j["kernel_ms_globaltimer"] >= j["device_ms_globaltimer"] > 0
+    e = j["e2e"]
+    assert abs(j["ms_per_step"] - e["value"]) / e["value"] < 0.05 and e["d2h_bytes_per_step"] == 48 + 120 * j["config"]["phases"]
+    r = j["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    cb = j["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["statistic"] == "median" and cb["value"] == cb["median_ms"] <= cb["mean_ms"] * 1.5
+    if n == 1:
+        assert r["bound"] == "hbm" and 0.9 < r["frac"] < 1.05
+    else:
+        assert r["bound"] == "nvlink" and j["value"] < 5.0
+        assert 700 < r["peak_measured_ce_bidi"] < 900 and 700 < r["peak_measured_ce_uni"] < 900
+        assert 0.8 < r["frac_read_of_ce_bidi"] < 1.0 and 0.8 < r["frac_write_of_ce_bidi"] < 1.0
+        # wire view: payload + protocol bytes of both directions' ops fill the 900 GB/s a direction has
+        assert 0.9 < r["frac_wire_read_phase_of_900"] < 1.0 and 0.85 < r["frac_wire_write_phase_of_900"] < 1.0
+        nv = j["nvlink_counters"]
+        assert abs(nv["tx_kib_delta"] / nv["algorithmic_kib_per_direction"] - 1) < 1e-3
+        g = j["per_link_gbps"]
+        assert g["read_min"] > g["gate_gbps_read"] > 500 and g["write_min"] > g["gate_gbps_write"] > 500
+        assert j["config"]["barriers"] == "neighbourhood"
+        if n == 8:
+            assert j["barrier_us"] < 80  # round 1: ~101-110 us with 15 all-rank exchanges
+
+
+@pytest.mark.parametrize("name,n,cfg", [("r02_bench_c2_n2.json", 2, "c2"), ("r02_bench_c3full_n8.json", 8, "c3-full")])
+def test_r02_config_lines(name, n, cfg):
+    j = load(name)
+    _common_r02(j, n)
+    assert j["config"]["config"] == cfg and j["config"]["mode"] == "full"
+    assert j["config"]["bytes_per_pair"] == j["config"]["bytes_per_gpu"] == ((64 << 20) if cfg == "c2" else (1 << 30))
+
+
+@pytest.mark.parametrize("n", [2, 8])
+def test_r02_storm_line(n):
+    j = load(f"r02_bench_c5_n{n}.json")
+    _common_r02(j, n)
+    st = j["storm"]
+    assert j["config"]["config"] == "c5" and st["cycles"] == j["steps"] and (n != 8 or st["cycles"] == 1000)
+    assert st["verdict_failures"] == 0 and st["device_free_delta_bytes"] == 0 and st["fd_delta"] == 0
+    assert st["cycle_ms_p99"] >= st["cycle_ms_p50"] >= st["probe_ms_p50"] > 0 and j["gpu_launches"] == st["cycles"] * n
