@@ -735,7 +735,9 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
         acc->t_end = 0ull;
       }
     }
-    __threadfence_system();
+    // The row lives in pinned host memory.  One release at system scope by thread 0 publishes it: the other
+    // threads' stores are ordered before it through the CTA barrier (cumulativity), so no per-thread
+    // fence.sys — each one is a round trip over PCIe (three of them cost the probe ~6 us per run).
     __syncthreads();
     if (t == 0) {
       row->t_first = *reinterpret_cast<volatile uint64_t*>(&ctrl->t_rel[0]);
@@ -744,7 +746,6 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
       row->n_phases = P.n_phases;
       row->t_enter = s_enter;
       row->t_exit = gtimer();
-      __threadfence_system();
       st_release_sys(const_cast<uint64_t*>(&row->done), P.run_seq);
     }
   }

@@ -15,6 +15,7 @@ fi
 if [ "$N" -gt 1 ]; then
   timeout 300 python tools/trace.py --gpus $N --out ${O}_trace_n$N.json > ${O}_trace_n$N.txt 2>&1; echo "trace exit=$?"
   timeout 300 python tools/trace.py --gpus $N --flags 0x400 --out ${O}_trace_allrank_n$N.json > ${O}_trace_allrank_n$N.txt 2>&1
+  timeout 300 python tools/trace.py --gpus $N --idle 1.0 --out ${O}_trace_cold_n$N.json > ${O}_trace_cold_n$N.txt 2>&1
   timeout 600 python tools/sweep.py --gpus $N --ctas 148 --iters 9 --overlap 1 --uni 0,1 --paths 0 --barriers 0,2,1 --out ${O}_barriers_n$N.jsonl > ${O}_barriers_n$N.log 2>&1
   echo "barrier sweep exit=$?"; cat ${O}_barriers_n$N.jsonl | cut -c1-400
 fi

@@ -16,10 +16,16 @@ ap.add_argument("--bytes", type=int, default=1 << 30)
 ap.add_argument("--mode", default="sliced")
 ap.add_argument("--flags", type=lambda x: int(x, 0), default=0)
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "trace.json"))
+ap.add_argument("--idle", type=float, default=0.0, help="sleep this long before the traced run (cold start: the daemon's case)")
 a = ap.parse_args()
 mode = {"sliced": 1, "full": 2, "reach": 0}[a.mode]
 with pkg.Open(pkg.Config(ordinals=list(range(a.gpus)), bytes=a.bytes, mode=mode, flags=a.flags, timeout_ms=20000)) as p:
     for _ in range(3):
+        r = p.Run()
+    if a.idle > 0:
+        import time
+
+        time.sleep(a.idle)
         r = p.Run()
     out = {"n": a.gpus, "mode": a.mode, "bytes": a.bytes, "flags": a.flags, "probe_ms": r.probe_ms,
            "device_ms": r.device_ms, "bpp": r.bytes_per_pair, "ranks": [p.Trace(i) for i in range(a.gpus)]}
@@ -30,4 +36,4 @@ with pkg.Open(pkg.Config(ordinals=list(range(a.gpus)), bytes=a.bytes, mode=mode,
         for ph in tr:
             d0 = (ph["t_end0"] - ph["t_start"]) / 1e3 if ph["t_end0"] else 0
             d1 = (ph["t_end1"] - ph["t_start"]) / 1e3 if ph["t_end1"] else 0
-            print(f"  {ph['job0']:6s}->{ph['peer0']:2d} {d0:8.1f} us | {ph['job1']:6s} {d1:8.1f} us | start {ph['t_start']/1e3:9.1f} arrive {ph['t_arrive']/1e3:9.1f} sync_all={ph['sync_all']}")
+            print(f"  {ph['job0']:6s}->{ph['peer0']:2d} {d0:8.1f} us | {ph['job1']:6s} {d1:8.1f} us | start {ph['t_start']/1e3:9.1f} arrive {ph['t_arrive']/1e3:9.1f} sync={ph['sync_mask']:#04x} post={ph['post_mask']:#04x}")
