@@ -558,14 +558,50 @@ def run_probe(args):
                         "read responses: 2 x (N-1) x bytes_per_pair"}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_subprocess(n)
-        print(json.dumps(line))
+    # every rank lets go of its buffers before the daemon twin takes the box (rank 0 only; the others wait in close())
     probe.Close()
+    grp.barrier()
+    if rank == 0:
+        if not args.no_daemon:
+            line["daemon_cost"]["daemon_process"] = daemon_once(n)
+        print(json.dumps(line))
     grp.close()
     if parity_ok is False:
         if rank == 0:
             sys.stderr.write("PARITY FAILURE: " + json.dumps(parity) + "\n")
         return 3
     return 0
+
+
+def daemon_once(n: int):
+    """What a daemon pod really pays: a FRESH process (`cdprobe-daemon run --once`, the C++ twin of the Go daemon's
+    probe slice) that creates the CUDA contexts of every visible GPU, opens the probe in one process, runs one cold
+    pass with the daemon's defaults (1 GiB per GPU, sliced, library gate) and writes its verdict.  Wall clock of the
+    process; not part of any timed region."""
+    import subprocess
+    import tempfile
+
+    exe = os.path.join(ROOT, "k8s-dra-driver-gpu_b200", "cdprobe-daemon")
+    lib = os.path.join(ROOT, "k8s-dra-driver-gpu_b200", "libcdprobe.so")
+    with tempfile.TemporaryDirectory() as td:
+        vp = os.path.join(td, "fabricprobe.json")
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "CUDA_VISIBLE_DEVICES")}
+        vis = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x] or [str(i) for i in range(n)]
+        env.update({"COMPUTE_DOMAIN_UUID": "bench", "CDPROBE_LIBRARY": lib, "FABRIC_PROBE_VERDICT_PATH": vp, "POD_UID": "bench",
+                    "CUDA_VISIBLE_DEVICES": ",".join(vis[:n])})  # the same N GPUs this bench line is about
+        try:
+            t0 = time.perf_counter()
+            cp = subprocess.run([exe, "run", "--once"], env=env, capture_output=True, text=True, timeout=300)
+            wall = (time.perf_counter() - t0) * 1e3
+            v = json.load(open(vp))
+            tp = [l for l in cp.stderr.splitlines() if l.startswith("t_fabric_probe")]
+            return {"wall_ms": wall, "exit": cp.returncode, "n_gpus": v["n"], "ok": v["ok"], "probe_ms": v["probe_ms"],
+                    "t_fabric_probe_s": float(tp[-1].split()[1]) if tp else None,
+                    "unreachable_pairs": v["unreachable_pairs"], "slow_pairs": v["slow_pairs"],
+                    "note": "fresh `cdprobe-daemon run --once` over every visible GPU in one process: CUDA context creation + "
+                            "cdprobe_open + one cold probe + verdict file"}
+        except Exception as e:
+            return {"wall_ms": None, "error": str(e)}
 
 
 def cpu_baseline_subprocess(n: int):
@@ -687,6 +723,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--timeout-ms", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-daemon", action="store_true", help="skip the fresh-process daemon timing (daemon_cost.daemon_process)")
     ap.add_argument("--config", default="", choices=["", "c2", "c3-full", "c5"],
                     help="BASELINE.json configs beyond the headline: c2 (2 GPUs, 64 MiB, full), c3-full (1 GiB per ordered "
                          "pair), c5 (reconcile storm: --steps cycles)")

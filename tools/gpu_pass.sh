@@ -1,6 +1,7 @@
 #!/bin/bash
 # One GPU pass on an N-GPU box (N = $1): gpu tests, per-phase trace, barrier-mode comparison, bench (both arms),
 # optional extra bench configs ($2..: c2 c3-full c5).  Everything lands in gpurun_out/ with the tag $TAG.
+# SKIP_TESTS=1 skips pytest, BENCH_ONLY=1 also skips traces and the barrier sweep, TESTS_K narrows pytest (-k).
 #   gpurun --gpus 2 --timeout 900 -- 'TAG=r02 tools/gpu_pass.sh 2 c2'
 N=${1:-1}; shift
 TAG=${TAG:-r02}
@@ -12,7 +13,7 @@ if [ -z "$SKIP_TESTS" ]; then
   timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 --timeout 400 -p no:cacheprovider ${TESTS_K:+-k "$TESTS_K"} > ${O}_pytest_n$N.log 2>&1
   echo "pytest exit=$?"; tail -12 ${O}_pytest_n$N.log
 fi
-if [ "$N" -gt 1 ]; then
+if [ "$N" -gt 1 ] && [ -z "$BENCH_ONLY" ]; then
   timeout 300 python tools/trace.py --gpus $N --out ${O}_trace_n$N.json > ${O}_trace_n$N.txt 2>&1; echo "trace exit=$?"
   timeout 300 python tools/trace.py --gpus $N --flags 0x400 --out ${O}_trace_allrank_n$N.json > ${O}_trace_allrank_n$N.txt 2>&1
   timeout 300 python tools/trace.py --gpus $N --idle 1.0 --out ${O}_trace_cold_n$N.json > ${O}_trace_cold_n$N.txt 2>&1
