@@ -13,7 +13,8 @@ torch.distributed (NCCL) is used only to bracket the timed region and take max-o
 
 metric  = nvlink_probe_ms (lower is better): time to produce the N x N reachability + GB/s
           matrix.  `value` is the probe kernel's duration by CUDA events on its launch stream
-          (max over ranks; buffers resident in HBM); `e2e.value` is the same probe through the
+          (median of the K timed steps, max over ranks; buffers resident in HBM; the mean and the worst
+          step are in `value_mean_ms` / `value_max_ms`); `e2e.value` is the same probe through the
           public C ABI call from the host: launch, kernel, result rows written to pinned host
           memory and read back.  Per-pair GB/s vs the 900 GB/s/dir NVLink-5 peak is in
           `per_link_gbps`; `roofline` is the dominant kernel against its bound (HBM at N = 1,
@@ -372,11 +373,17 @@ def run_probe(args):
 
     wall_ms = max_over_ranks(t_local)
     ms_per_step = wall_ms / args.steps
-    value = max_over_ranks(statistics.mean(ev))
-    device_ms = max_over_ranks(statistics.mean(dev_ms))
-    e2e_ms = max_over_ranks(statistics.mean(host_ms))
+    # `value` is the typical probe: the MEDIAN of the K event-timed kernels (max over ranks), like the reference arm's
+    # median poll.  One host hiccup in K steps (a rank launching a few ms late parks every other rank's kernel in the
+    # opening barrier) moves the mean by tens of us; the mean and the worst step ride beside it.
+    value = max_over_ranks(statistics.median(ev))
+    value_mean = max_over_ranks(statistics.mean(ev))
+    value_max = max_over_ranks(max(ev))
+    device_ms = max_over_ranks(statistics.median(dev_ms))
+    e2e_ms = max_over_ranks(statistics.median(host_ms))
+    e2e_mean = max_over_ranks(statistics.mean(host_ms))
     barrier_us = max_over_ranks(statistics.median(bar_us))
-    kernel_ms = max_over_ranks(statistics.mean(ker_ms))
+    kernel_ms = max_over_ranks(statistics.median(ker_ms))
 
     # per-pair GB/s over the whole domain: the last timed step's rows, completed across ranks
     rc = abi.load_library().cdprobe_gather(probe._h, ctypes.byref(out))
@@ -508,6 +515,7 @@ def run_probe(args):
         wl = conf["name"].format(n=n, cycles=0) if conf else workload_name(n, args.mode, args.bytes)
         line = {
             "metric": "nvlink_probe_ms", "value": value, "unit": "ms", "n_gpus": n, "steps": args.steps,
+            "value_statistic": "median of the timed steps (max over ranks)", "value_mean_ms": value_mean, "value_max_ms": value_max,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {
@@ -524,7 +532,7 @@ def run_probe(args):
                                    ">= device_ms (first barrier release -> last phase done); the differences are launch/"
                                    "completion latency and the residency barrier + row output",
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 2768,
-                    "d2h_bytes_per_step": 48 + 120 * int(res.phases),
+                    "d2h_bytes_per_step": 48 + 120 * int(res.phases), "mean_ms": e2e_mean,
                     "note": "cdprobe_run from a host thread: kernel parameters (2768 B) in, result row "
                             "(pinned host memory written by the kernel) out; the probe's inputs are "
                             "generated on the device by design"},
