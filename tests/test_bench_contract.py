@@ -85,14 +85,17 @@ def _common_r02(j, n):
     assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-@pytest.mark.parametrize("n", [1, 2, 8])
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
 def test_r02_headline_line(n):
     j = load(f"r02_bench_n{n}.json")
     _common_r02(j, n)
     assert j["gpu_launches"] == j["steps"] * n
-    assert j["value"] >= j.get("kernel_ms_globaltimer", j["device_ms_globaltimer"]) >= j["device_ms_globaltimer"] > 0
+    assert j["value"] >= j["kernel_ms_globaltimer"] >= j["device_ms_globaltimer"] > 0
     e = j["e2e"]
-    assert abs(j["ms_per_step"] - e["value"]) / e["value"] < 0.05
+    assert abs(j["ms_per_step"] - e["value"]) / e["value"] < 0.05 and e["d2h_bytes_per_step"] == 48 + 120 * j["config"]["phases"]
+    dp = j["daemon_cost"]["daemon_process"]  # a fresh `cdprobe-daemon run --once` over the same N GPUs
+    assert dp["exit"] == 0 and dp["ok"] is True and dp["n_gpus"] == n and dp["unreachable_pairs"] == dp["slow_pairs"] == 0
+    assert dp["wall_ms"] > dp["probe_ms"] > 0
     r = j["roofline"]
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     cb = j["cpu_baseline"]
@@ -104,15 +107,15 @@ def test_r02_headline_line(n):
         assert 700 < r["peak_measured_ce_bidi"] < 900 and 700 < r["peak_measured_ce_uni"] < 900
         assert 0.8 < r["frac_read_of_ce_bidi"] < 1.0 and 0.8 < r["frac_write_of_ce_bidi"] < 1.0
         # wire view: payload + protocol bytes of both directions' ops fill the 900 GB/s a direction has
-        if "frac_wire_read_phase_of_900" in r:
-            assert 0.9 < r["frac_wire_read_phase_of_900"] < 1.0 and 0.85 < r["frac_wire_write_phase_of_900"] < 1.0
+        assert 0.9 < r["frac_wire_read_phase_of_900"] < 1.0 and 0.85 < r["frac_wire_write_phase_of_900"] < 1.0
         nv = j["nvlink_counters"]
         assert abs(nv["tx_kib_delta"] / nv["algorithmic_kib_per_direction"] - 1) < 1e-3
         g = j["per_link_gbps"]
         assert g["read_min"] > g["gate_gbps_read"] > 500 and g["write_min"] > g["gate_gbps_write"] > 500
         assert j["config"]["barriers"] == "neighbourhood"
         if n == 8:
-            assert j["barrier_us"] < 80  # round 1: ~101-110 us with 15 all-rank exchanges
+            assert j["barrier_us"] < 60  # round 1: ~93-110 us with 15 all-rank exchanges
+            assert j["value"] < 3.30    # round 1: 3.328-3.330 ms
 
 
 @pytest.mark.parametrize("name,n,cfg", [("r02_bench_c2_n2.json", 2, "c2"), ("r02_bench_c3full_n8.json", 8, "c3-full")])

@@ -20,7 +20,7 @@ def load(name):
     return json.loads([l for l in open(p) if l.startswith("{")][-1])
 
 
-print("| N | probe ms (CUDA events) | e2e ms (host call) | flag barriers per probe | pair GB/s, both directions loaded: read · write | one way: read · write (probe ms) | same-box copy engine: one way · both ways | cold probe after 1 s idle | open + first verdict | reference CPU poll, median (mean) |")
+print("| N | probe ms (CUDA events) | e2e ms (host call) | flag barriers per probe | pair GB/s, both directions loaded: read · write | one way: read · write (probe ms) | same-box copy engine: one way · both ways | cold probe after 1 s idle | first verdict: open + cold run · fresh daemon process over the N GPUs | reference CPU poll, median (mean) |")
 print("|---|---|---|---|---|---|---|---|---|---|")
 for n in (1, 2, 4, 8):
     b, r = load(f"{prefix}{mid}_bench_n{n}.json"), load(f"{prefix}{mid}_ref_n{n}.json")
@@ -41,6 +41,8 @@ for n in (1, 2, 4, 8):
     bar = f"{b['barrier_us']:.0f} µs" if "barrier_us" in b else "—"
     dc = b.get("daemon_cost")
     first = f"{dc['cold_first_verdict_ms']:.0f} ms" if dc else "—"
+    if dc and dc.get("daemon_process", {}).get("wall_ms"):
+        first += f" · {dc['daemon_process']['wall_ms'] / 1e3:.1f} s"
     if not r:
         ref = "—"
     elif r["cpu_baseline"].get("statistic") == "median":
