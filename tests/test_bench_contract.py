@@ -134,3 +134,60 @@ def test_r02_storm_line(n):
     assert j["config"]["config"] == "c5" and st["cycles"] == j["steps"] and (n != 8 or st["cycles"] == 1000)
     assert st["verdict_failures"] == 0 and st["device_free_delta_bytes"] == 0 and st["fd_delta"] == 0
     assert st["cycle_ms_p99"] >= st["cycle_ms_p50"] >= st["probe_ms_p50"] > 0 and j["gpu_launches"] == st["cycles"] * n
+
+
+# ---- the parity self-check of bench.py is not vacuous: a wrong checksum or a wrong reach bit is caught -------------
+def test_parity_block_catches_mismatches(pkg, oracle, monkeypatch):
+    import types
+
+    import bench
+
+    n, nbytes, mode = 3, 3 << 12, 1
+    bpp = oracle.plan(n, nbytes, mode).bytes_per_pair
+    words = bpp // 8
+    seed, run_seq = oracle.DEFAULT_SEED, 7
+
+    def result():
+        r = types.SimpleNamespace(bytes_per_pair=bpp, run_seq=run_seq)
+        z = [[0] * n for _ in range(n)]
+        r.sum_read, r.xor_read, r.sum_write, r.xor_write = ([row[:] for row in z] for _ in range(4))
+        r.reach = [[1] * n for _ in range(n)]
+        for i in range(n):
+            for j in range(n):
+                if i != j:
+                    r.sum_read[i][j], r.xor_read[i][j] = oracle.expected_read(seed, n, nbytes, mode, i, j)
+                    r.sum_write[i][j], r.xor_write[i][j] = oracle.write_checksum(seed, i, j, run_seq, words)
+        return r
+
+    # no NVML in this container: the reach half must say so (None), never assume
+    good = bench.parity_block(pkg, oracle, result(), n, nbytes, mode, [f"GPU-{i}" for i in range(n)], seed)
+    assert good["cells"] == 6 and good["checksum_ok"] is True and good["reach_vs_nvml_ok"] is None and good["reach_vs_nvml_error"]
+    bad = result()
+    bad.xor_write[2][0] ^= 1 << 40
+    blk = bench.parity_block(pkg, oracle, bad, n, nbytes, mode, [f"GPU-{i}" for i in range(n)], seed)
+    assert blk["checksum_ok"] is False and blk["checksum_mismatches"] == [["write", 2, 0]]
+    # with an NVML that answers (the fake one): an unreachable cell the NVML poll calls reachable is a parity failure
+    fake = types.SimpleNamespace(uuids=lambda: [f"GPU-{i}" for i in range(n)], reach_matrix=lambda: [[1] * n for _ in range(n)], n=n)
+    monkeypatch.setattr(oracle, "nvml_poll", lambda *a, **k: fake)
+    r = result()
+    assert bench.parity_block(pkg, oracle, r, n, nbytes, mode, [f"GPU-{i}" for i in (2, 0, 1)], seed)["reach_vs_nvml_ok"] is True
+    r.reach[1][2] = 0
+    blk = bench.parity_block(pkg, oracle, r, n, nbytes, mode, [f"GPU-{i}" for i in range(n)], seed)
+    assert blk["reach_vs_nvml_ok"] is False and blk["reach_mismatches"] == [[1, 2, 0, 1]]
+
+
+@pytest.mark.gpu
+def test_bench_runs_end_to_end_with_parity(tmp_path):
+    """bench.py itself on the GPU box (N = 1, a few steps): exit 0, one JSON line, parity block green, roofline
+    against the measured peak — what the driver runs, exercised by `pytest -m gpu` too."""
+    import subprocess
+    import sys
+
+    cp = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "10", "--warmup", "3",
+                         "--no-cpu-baseline", "--no-daemon"], capture_output=True, text=True, timeout=300)
+    assert cp.returncode == 0, cp.stderr[-2000:]
+    lines = [l for l in cp.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["n_gpus"] == 1 and j["gpu_launches"] == 10 and j["parity"]["checksum_ok"] is True
+    assert j["parity"]["reach_vs_nvml_ok"] is True and j["verdict"] is True and 0.5 < j["roofline"]["frac"] < 1.1

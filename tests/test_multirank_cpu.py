@@ -29,7 +29,7 @@ CHILD = textwrap.dedent(
     lib = m.abi.load_library()
     rc = lib.cdprobe_rendezvous_selftest(g.session("t").encode(), g.rank, g.world, 20000)
     out = {"rank": g.rank, "world": g.world, "max": g.max(10.0 + g.rank), "min": g.min(10.0 + g.rank),
-           "session": g.session(), "rdv": rc}
+           "session": g.session(), "rdv": rc, "uuids": g.gather_objects(f"GPU-{g.rank:04d}")}
     g.close()
     print("OUT " + json.dumps(out))
     """
@@ -56,6 +56,7 @@ def test_gloo_rank_group_world2(pkg):
     assert sorted(o["rank"] for o in outs) == [0, 1]
     for o in outs:
         assert o["world"] == 2 and o["max"] == 11.0 and o["min"] == 10.0 and o["rdv"] == 0
+        assert o["uuids"] == ["GPU-0000", "GPU-0001"]  # rank order on every rank: bench.py's UUID -> NVML index matching
     assert outs[0]["session"] == outs[1]["session"]  # every rank derives the same rendezvous name
 
 
