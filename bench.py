@@ -114,7 +114,8 @@ class ClockSampler(threading.Thread):
 
 
 def nvlink_counters(index: int):
-    """Aggregate NVLink data TX/RX KiB of one GPU (NVML field values 138/139), or None."""
+    """NVLink data TX/RX KiB of one GPU through NVML field values 138/139: the aggregate over its links
+    (scopeId 0xFFFFFFFF) and each of the 18 physical links (scopeId = link) — or None."""
     try:
         import pynvml
 
@@ -122,14 +123,28 @@ def nvlink_counters(index: int):
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
         out = {}
         for name, fid in (("tx_kib", 138), ("rx_kib", 139)):
-            vals = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)])
-            v = vals[0]
-            if v.nvmlReturn != 0:
+            vals = pynvml.nvmlDeviceGetFieldValues(h, [(fid, 0xFFFFFFFF)] + [(fid, l) for l in range(18)])
+            if vals[0].nvmlReturn != 0:
                 return None
-            out[name] = int(v.value.ullVal)
+            out[name] = int(vals[0].value.ullVal)
+            out[name + "_per_link"] = [int(v.value.ullVal) if v.nvmlReturn == 0 else None for v in vals[1:]]
         return out
     except Exception:
         return None
+
+
+def per_link_delta(a, b, key):
+    """Per physical link KiB moved between two samples, and how evenly the GPU spread them over its links."""
+    x, y = a.get(key + "_per_link"), b.get(key + "_per_link")
+    if not x or not y or any(v is None for v in x + y):
+        return None
+    d = [q - p for p, q in zip(x, y)]
+    active = [v for v in d if v > 0]
+    if not active:
+        return None
+    mean = sum(active) / len(active)
+    return {"kib": d, "links_carrying_traffic": len(active), "min_share_of_mean": min(active) / mean,
+            "max_share_of_mean": max(active) / mean}
 
 
 def dist_env():
@@ -561,9 +576,13 @@ def run_probe(args):
             line["nvlink_counters"] = {
                 "tx_kib_delta": nvl1["tx_kib"] - nvl0["tx_kib"], "rx_kib_delta": nvl1["rx_kib"] - nvl0["rx_kib"],
                 "algorithmic_kib_per_direction": (2 * args.steps + 2) * 2 * a_gpu // 1024,
+                "per_physical_link_tx": per_link_delta(nvl0, nvl1, "tx_kib"),
+                "per_physical_link_rx": per_link_delta(nvl0, nvl1, "rx_kib"),
                 "note": "NVML fields 138/139 (NVLink data TX/RX KiB) on rank 0's GPU across both timed loops "
                         "(2 x steps + 2 probes); per probe each direction carries the write payload and the "
-                        "read responses: 2 x (N-1) x bytes_per_pair"}
+                        "read responses: 2 x (N-1) x bytes_per_pair.  per_physical_link_*: the same counters per link "
+                        "(scopeId = link 0..17): a port spreads a pair's traffic over all its links, so a weak link "
+                        "shows up here as an outlier share before it shows in the pair's GB/s"}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_subprocess(n)
     # every rank lets go of its buffers before the daemon twin takes the box (rank 0 only; the others wait in close())

@@ -262,7 +262,7 @@ CDPROBE_API const char* cdprobe_last_error(void);
  *   cdprobe_remap_peer / cdprobe_unmap_peer  emulate NodeUnprepare/NodePrepare churn around a live domain:
  *                                                                   cmd/compute-domain-kubelet-plugin/driver.go:165-232
  *   cdprobe_gather, cdprobe_info, cdprobe_trace, cdprobe_set_option, cdprobe_corrupt, cdprobe_plan,
- *   cdprobe_schedule, cdprobe_ce_copy, cdprobe_rendezvous_selftest: diagnostics, benches, fault injection; the reference has
+ *   cdprobe_schedule, cdprobe_gate, cdprobe_ce_copy, cdprobe_rendezvous_selftest: diagnostics, benches, fault injection; the reference has
  *   no counterpart (it has no probe).
  */
 CDPROBE_API int cdprobe_open(const cdprobe_config_t* cfg, cdprobe_t** out);
@@ -313,6 +313,9 @@ CDPROBE_API int cdprobe_topology(uint32_t strict, cdprobe_topology_t* out);
 CDPROBE_API int cdprobe_schedule(uint32_t n, uint32_t rank, uint64_t bytes, uint32_t mode, uint32_t ops, uint32_t flags,
                                  uint32_t ctas, uint32_t verify_ctas, cdprobe_schedule_t* out);
 CDPROBE_API int cdprobe_rendezvous_selftest(const char* session, uint32_t rank, uint32_t world, uint32_t timeout_ms);
+/* The GB/s gate cdprobe_run would apply to reads / writes for this configuration in an n-rank domain (0: bandwidth is
+ * not judged — reach-only mode, n == 1).  Host-only arithmetic: lets a caller log or test the threshold without a GPU. */
+CDPROBE_API int cdprobe_gate(const cdprobe_config_t* cfg, uint32_t n_total, float* gate_read_gbps, float* gate_write_gbps);
 
 #ifdef __cplusplus
 }

@@ -19,8 +19,9 @@ from .fabricprobe import (  # noqa: F401
     ProbeError,
     Result,
     Open,
+    gate,
     plan,
     topology,
 )
 
-__all__ = ["abi", "build", "Config", "Probe", "ProbeError", "ErrUnsupported", "Result", "Open", "plan", "topology"]
+__all__ = ["abi", "build", "Config", "Probe", "ProbeError", "ErrUnsupported", "Result", "Open", "gate", "plan", "topology"]

@@ -206,6 +206,7 @@ SYMBOLS = {
     "cdprobe_schedule": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.c_uint32, C.POINTER(ScheduleT)]),
     "cdprobe_rendezvous_selftest": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "cdprobe_gate": (C.c_int, [C.POINTER(ConfigT), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcdprobe.so")

@@ -650,16 +650,17 @@ struct HealthyRates {  // GB/s per direction per GPU, 1 GiB transfers
   double read_bidi = 672.0, write_bidi = 703.0, read_uni = 785.0, write_uni = 714.7;
   double phase_overhead_ns = 8000.0;
 };
-static float gate_gbps(const cdprobe* h, bool is_read) {
-  if (h->cfg.mode == CDPROBE_MODE_REACH_ONLY || h->n_total <= 1) return 0.f;
-  if (h->cfg.link_peak_gbps > 0.f) return (h->cfg.min_fraction > 0.f ? h->cfg.min_fraction : 0.65f) * h->cfg.link_peak_gbps;
+static float gate_gbps_for(const cdprobe_config_t& cfg, uint32_t n_total, uint64_t bpp, bool is_read) {
+  if (cfg.mode == CDPROBE_MODE_REACH_ONLY || n_total <= 1) return 0.f;
+  if (cfg.link_peak_gbps > 0.f) return (cfg.min_fraction > 0.f ? cfg.min_fraction : 0.65f) * cfg.link_peak_gbps;
   const HealthyRates hr;
-  const bool uni = (h->cfg.flags & CDPROBE_FLAG_UNIDIRECTIONAL) != 0;
+  const bool uni = (cfg.flags & CDPROBE_FLAG_UNIDIRECTIONAL) != 0;
   const double rate = is_read ? (uni ? hr.read_uni : hr.read_bidi) : (uni ? hr.write_uni : hr.write_bidi);
-  const double bpp = (double)h->plan.bpp;
-  const double expected = bpp / (bpp / rate + hr.phase_overhead_ns);  // bytes per ns == GB/s
-  return (float)((h->cfg.min_fraction > 0.f ? h->cfg.min_fraction : 0.90f) * expected);
+  const double b = (double)bpp;
+  const double expected = b / (b / rate + hr.phase_overhead_ns);  // bytes per ns == GB/s
+  return (float)((cfg.min_fraction > 0.f ? cfg.min_fraction : 0.90f) * expected);
 }
+static float gate_gbps(const cdprobe* h, bool is_read) { return gate_gbps_for(h->cfg, h->n_total, h->plan.bpp, is_read); }
 
 static void assemble(const cdprobe* h, cdprobe_result_t* out) {
   const Plan& pl = h->plan;
@@ -1172,6 +1173,18 @@ int cdprobe_ce_copy(cdprobe_t* h, uint32_t n_copies, const uint32_t* local, cons
     CDP_RT(cudaEventElapsedTime(&ms, L.ev0, L.ev1));
     ms_out[k] = ms;
   }
+  return CDPROBE_OK;
+}
+
+int cdprobe_gate(const cdprobe_config_t* cfg, uint32_t n_total, float* gate_read_gbps, float* gate_write_gbps) {
+  if (cfg == nullptr || gate_read_gbps == nullptr || gate_write_gbps == nullptr) return CDPROBE_ERR_ARG;
+  if (cfg->abi != CDPROBE_ABI_VERSION) return CDPROBE_ERR_ABI;
+  if (cfg->link_peak_gbps < 0.f || cfg->min_fraction < 0.f) return CDPROBE_ERR_ARG;
+  cdp::Plan pl;
+  const int rc = cdp::make_plan(n_total, cfg->bytes, cfg->mode, cfg->flags, &pl);
+  if (rc != CDPROBE_OK) return rc;
+  *gate_read_gbps = cdp::gate_gbps_for(*cfg, n_total, pl.bpp, true);
+  *gate_write_gbps = cdp::gate_gbps_for(*cfg, n_total, pl.bpp, false);
   return CDPROBE_OK;
 }
 

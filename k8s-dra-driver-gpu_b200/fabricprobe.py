@@ -276,6 +276,17 @@ def topology(strict: bool = True) -> abi.TopologyT:
     return t
 
 
+def gate(cfg: Config, n_total: int):
+    """(read, write) GB/s threshold the verdict of an n_total-rank domain with this config applies (host-only)."""
+    lib = abi.load_library()
+    r, w = C.c_float(), C.c_float()
+    c = cfg.to_c()
+    rc = lib.cdprobe_gate(C.byref(c), n_total, C.byref(r), C.byref(w))
+    if rc != abi.OK:
+        _raise(lib, rc, "cdprobe_gate")
+    return r.value, w.value
+
+
 def plan(n: int, nbytes: int, mode: int, flags: int = 0) -> abi.PlanT:
     lib = abi.load_library()
     p = abi.PlanT()
