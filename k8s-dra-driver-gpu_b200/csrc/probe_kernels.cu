@@ -9,8 +9,11 @@
 //                   and pushes it into the peer's landing slot with TMA bulk
 //                   stores (cp.async.bulk.global.shared::cta) or st.global.v4/.v8.
 // K3 barrier      : grid barrier (atomic arrive / release word) whose last
-//                   arriver runs the cross-GPU flag barrier: one fence.sys,
-//                   pipelined st.relaxed.sys epochs into every peer's Ctrl,
+//                   arriver runs the cross-GPU flag exchange with the ranks the
+//                   phase table names (at most four between rounds, nobody between
+//                   the write and the read of a round, everybody at open/close):
+//                   publish, one fence.sys only if something was published,
+//                   pipelined st.relaxed.sys epochs into those peers' Ctrl,
 //                   ld.acquire.sys on the local copy.
 // K4 verify/local : the read probe pointed at local HBM (landing slots, source
 //                   slices at open, the N = 1 loop-back).
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(kThreads, 1) cdprobe_kernel(const __grid_const
     }
     // The row lives in pinned host memory.  One release at system scope by thread 0 publishes it: the other
     // threads' stores are ordered before it through the CTA barrier (cumulativity), so no per-thread
-    // fence.sys — each one is a round trip over PCIe (three of them cost the probe ~6 us per run).
+    // fence.sys — each one is a round trip over PCIe (round 1 had three of them here: ~5 us per run, 512 -> 507 us at N = 1).
     __syncthreads();
     if (t == 0) {
       row->t_first = *reinterpret_cast<volatile uint64_t*>(&ctrl->t_rel[0]);

@@ -110,6 +110,10 @@ def test_r02_headline_line(n):
         assert 0.9 < r["frac_wire_read_phase_of_900"] < 1.0 and 0.85 < r["frac_wire_write_phase_of_900"] < 1.0
         nv = j["nvlink_counters"]
         assert abs(nv["tx_kib_delta"] / nv["algorithmic_kib_per_direction"] - 1) < 1e-3
+        if nv.get("per_physical_link_tx"):  # the 18 links of the port carry equal shares (a weak link would stand out)
+            pl = nv["per_physical_link_tx"]
+            assert pl["links_carrying_traffic"] == 18 and sum(pl["kib"]) == nv["tx_kib_delta"]
+            assert 0.98 < pl["min_share_of_mean"] <= 1.0 <= pl["max_share_of_mean"] < 1.02
         g = j["per_link_gbps"]
         assert g["read_min"] > g["gate_gbps_read"] > 500 and g["write_min"] > g["gate_gbps_write"] > 500
         assert j["config"]["barriers"] == "neighbourhood"
