@@ -7,6 +7,7 @@
 // type of the file the C++ twin writes against them, so either `run` can feed either `check`.
 //
 // Wiring (INTEGRATION.md §2 has the main.go hunks):
+//   newApp(): cliFlags = append(cliFlags, fabricProbeCLIFlags()...)   // next to featureGateConfig.Flags(), main.go:166
 //   run():   after addComputeDomainCliqueLabel(), BEFORE the `if flags.cliqueID == ""` early wait
 //            (main.go:244-250) so single-node HGX boxes are covered too:
 //                prober := startFabricProbe(ctx, flags)
@@ -31,6 +32,7 @@ import (
 	"strings"
 	"time"
 
+	"github.com/urfave/cli/v2"
 	"k8s.io/klog/v2"
 
 	"sigs.k8s.io/dra-driver-nvidia-gpu/pkg/fabricprobe"
@@ -45,6 +47,76 @@ const (
 	fabricProbeVerdictPath   = "/imexd/fabricprobe.json"
 	fabricProbeVerdictSchema = 2
 )
+
+// fabricProbeOptions are the probe's own flags.  They live in this file (package-level, filled by urfave/cli through
+// Destination pointers exactly like the fields of Flags, main.go:104-166) so that the patch to main.go stays one
+// appended line; podUID and nodeName come from the existing Flags.
+type fabricProbeOptions struct {
+	bytes        uint64
+	mode         string
+	minFraction  float64
+	linkPeakGBps float64
+	intervalS    int
+	maxAgeS      int
+}
+
+var fpOpts fabricProbeOptions
+
+func fabricProbeCLIFlags() []cli.Flag {
+	return []cli.Flag{
+		&cli.Uint64Flag{
+			Name:        "fabric-probe-bytes",
+			Usage:       "Per-GPU buffer the fabric probe moves (bytes).",
+			Value:       1 << 30,
+			EnvVars:     []string{"FABRIC_PROBE_BYTES"},
+			Destination: &fpOpts.bytes,
+		},
+		&cli.StringFlag{
+			Name:        "fabric-probe-mode",
+			Usage:       "sliced (bytes split over the peers), full (bytes per ordered pair) or reach-only.",
+			Value:       "sliced",
+			EnvVars:     []string{"FABRIC_PROBE_MODE"},
+			Destination: &fpOpts.mode,
+		},
+		&cli.Float64Flag{
+			Name:        "fabric-probe-min-fraction",
+			Usage:       "Bandwidth gate as a fraction of the reference figure; 0 = library default.",
+			EnvVars:     []string{"FABRIC_PROBE_MIN_FRACTION"},
+			Destination: &fpOpts.minFraction,
+		},
+		&cli.Float64Flag{
+			Name:        "fabric-probe-link-peak-gbps",
+			Usage:       "Reference figure of the gate in GB/s; 0 = the library's calibrated B200 reference.",
+			EnvVars:     []string{"FABRIC_PROBE_LINK_PEAK_GBPS"},
+			Destination: &fpOpts.linkPeakGBps,
+		},
+		&cli.IntFlag{
+			Name:        "fabric-probe-interval",
+			Usage:       "Seconds between periodic probe passes; 0 = only at start and on daemon-set changes.",
+			EnvVars:     []string{"FABRIC_PROBE_INTERVAL_S"},
+			Destination: &fpOpts.intervalS,
+		},
+		&cli.IntFlag{
+			Name:        "fabric-probe-max-age",
+			Usage:       "check fails when the verdict is older than this many seconds; 0 = 3 x interval + 60 when an interval is set, else never.",
+			EnvVars:     []string{"FABRIC_PROBE_MAX_AGE_S"},
+			Destination: &fpOpts.maxAgeS,
+		},
+	}
+}
+
+func (o *fabricProbeOptions) modeID() uint32 {
+	switch o.mode {
+	case "full":
+		return fabricprobe.ModeFull
+	case "reach-only":
+		return fabricprobe.ModeReachOnly
+	default:
+		return fabricprobe.ModeSliced
+	}
+}
+
+func (o *fabricProbeOptions) interval() time.Duration { return time.Duration(o.intervalS) * time.Second }
 
 // fabricProbeVerdict is the file `run` writes and `check` reads.  Reach matrices are 0/1 integers
 // (a []bool would marshal as true/false and a []uint8 as base64; the C++ twin prints integers).
@@ -113,7 +185,7 @@ func boolsToInts(b []bool) []int {
 }
 
 // startFabricProbe removes a stale verdict, opens the probe and runs it once; further passes happen on
-// Kick() (daemon-set changes) and every flags.fabricProbeInterval when that is set.  It returns at
+// Kick() (daemon-set changes) and every FABRIC_PROBE_INTERVAL_S seconds when that is set.  It returns at
 // once; Stop() waits for the goroutine (which exits on ctx cancel) and closes the handle.
 func startFabricProbe(ctx context.Context, flags *Flags) *fabricProber {
 	p := &fabricProber{}
@@ -125,10 +197,10 @@ func startFabricProbe(ctx context.Context, flags *Flags) *fabricProber {
 		klog.Warningf("cannot remove stale %s: %v", fabricProbeVerdictPath, err)
 	}
 	cfg := fabricprobe.Config{
-		Bytes:        flags.fabricProbeBytes,       // FABRIC_PROBE_BYTES, default 1 GiB
-		Mode:         flags.fabricProbeMode,        // FABRIC_PROBE_MODE, default sliced
-		MinFraction:  flags.fabricProbeMinFraction, // FABRIC_PROBE_MIN_FRACTION, 0 = library default
-		LinkPeakGBps: flags.fabricProbeLinkPeak,    // FABRIC_PROBE_LINK_PEAK_GBPS, 0 = calibrated reference
+		Bytes:        fpOpts.bytes,                 // FABRIC_PROBE_BYTES, default 1 GiB
+		Mode:         fpOpts.modeID(),              // FABRIC_PROBE_MODE, default sliced
+		MinFraction:  float32(fpOpts.minFraction),  // FABRIC_PROBE_MIN_FRACTION, 0 = library default
+		LinkPeakGBps: float32(fpOpts.linkPeakGBps), // FABRIC_PROBE_LINK_PEAK_GBPS, 0 = calibrated reference
 		TimeoutMs:    5000,
 		Flags:        fabricprobe.FlagFabricHandles | fabricprobe.FlagMigAware,
 	}
@@ -180,8 +252,8 @@ func startFabricProbe(ctx context.Context, flags *Flags) *fabricProber {
 			}
 		}()
 		var tick <-chan time.Time
-		if flags.fabricProbeInterval > 0 {
-			t := time.NewTicker(flags.fabricProbeInterval)
+		if fpOpts.interval() > 0 {
+			t := time.NewTicker(fpOpts.interval())
 			defer t.Stop()
 			tick = t.C
 		}
@@ -209,7 +281,8 @@ func writeVerdict(res fabricprobe.Result, runErr error, flags *Flags) fabricProb
 		GateGBpsRead: res.GateGBpsRead, GateGBpsWrite: res.GateGBpsWrite,
 		ProbeMs: res.ProbeMs, BytesPerPair: res.BytesPerPair,
 		ReachRead: boolsToInts(res.ReachRead), ReachWrite: boolsToInts(res.ReachWrite),
-		GBpsRead: res.GBpsRead, GBpsWrite: res.GBpsWrite,
+		// never nil: an empty result marshals as [] like the C++ twin writes it, not as null
+		GBpsRead: append([]float32{}, res.GBpsRead...), GBpsWrite: append([]float32{}, res.GBpsWrite...),
 	}
 	if runErr != nil {
 		v.Error = runErr.Error()
@@ -244,9 +317,9 @@ func checkFabricProbeVerdict(flags *Flags) error {
 	if b := bootID(); v.BootID != "" && b != "" && v.BootID != b {
 		return nil
 	}
-	maxAge := flags.fabricProbeMaxAge // FABRIC_PROBE_MAX_AGE_S
-	if maxAge <= 0 && flags.fabricProbeInterval > 0 {
-		maxAge = 3*flags.fabricProbeInterval + time.Minute // periodic re-probe on: a verdict must keep coming
+	maxAge := time.Duration(fpOpts.maxAgeS) * time.Second // FABRIC_PROBE_MAX_AGE_S
+	if maxAge <= 0 && fpOpts.interval() > 0 {
+		maxAge = 3*fpOpts.interval() + time.Minute // periodic re-probe on: a verdict must keep coming
 	}
 	if age := time.Since(time.Unix(v.TimeUnix, 0)); maxAge > 0 && age > maxAge {
 		return fmt.Errorf("fabric probe verdict is stale (%d s old)", int(age.Seconds()))

@@ -15,7 +15,9 @@
 package fabricprobe
 
 /*
+#cgo CFLAGS: -I${SRCDIR}
 #cgo LDFLAGS: -ldl
+// cdprobe.h (this repository's include/cdprobe.h) is vendored next to this file.
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdlib.h>
