@@ -235,6 +235,7 @@ typedef struct {
   char pci_bus_id[CDPROBE_MAX_GPUS][32];
   uint8_t mig[CDPROBE_MAX_GPUS];                  /* MIG mode currently enabled */
   uint8_t links_active[CDPROBE_MAX_GPUS];         /* NvLinkState == ENABLED over the 18 links */
+  uint32_t link_mask[CDPROBE_MAX_GPUS];           /* bit l set: link l is ENABLED (which physical link is down, not only how many) */
   uint8_t fabric_state[CDPROBE_MAX_GPUS];         /* nvmlGpuFabricInfo_t.state */
   char clique_id[96];                             /* "<clusterUUID>.<cliqueId>" or "" (nvlib.go:208-363) */
   char clique_error[160];                         /* non-empty: getCliqueID would return this error */

@@ -25,6 +25,7 @@ type GPUTopology struct {
 	PCIBusID    string
 	MigEnabled  bool
 	LinksActive int
+	LinkMask    uint32 // bit l set: NVLink l is ENABLED
 	FabricState uint8
 }
 
@@ -66,6 +67,7 @@ func EnumerateTopology(lib nvml.Interface, strict bool) (*NodeTopology, error) {
 		for l := 0; l < nvlinkMaxLinks; l++ {
 			if st, ret := dev.GetNvLinkState(l); ret == nvml.SUCCESS && st == nvml.FEATURE_ENABLED {
 				g.LinksActive++
+				g.LinkMask |= 1 << uint(l)
 			}
 		}
 		info, ret := dev.GetGpuFabricInfo()

@@ -159,6 +159,7 @@ class TopologyT(C.Structure):
         ("pci_bus_id", (C.c_char * 32) * MAX_GPUS),
         ("mig", C.c_uint8 * MAX_GPUS),
         ("links_active", C.c_uint8 * MAX_GPUS),
+        ("link_mask", C.c_uint32 * MAX_GPUS),
         ("fabric_state", C.c_uint8 * MAX_GPUS),
         ("clique_id", C.c_char * 96),
         ("clique_error", C.c_char * 160),

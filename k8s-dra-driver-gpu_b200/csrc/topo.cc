@@ -110,7 +110,10 @@ extern "C" int cdprobe_topology(uint32_t strict, cdprobe_topology_t* out) {
     out->mig[i] = (nv.mig_(d, &cur, &pend) == NVML_SUCCESS && cur == NVML_DEVICE_MIG_ENABLE) ? 1 : 0;
     for (unsigned int l = 0; l < CDPROBE_NVLINK_MAX_LINKS; ++l) {
       nvmlEnableState_t st = NVML_FEATURE_DISABLED;
-      if (nv.link_(d, l, &st) == NVML_SUCCESS && st == NVML_FEATURE_ENABLED) out->links_active[i]++;
+      if (nv.link_(d, l, &st) == NVML_SUCCESS && st == NVML_FEATURE_ENABLED) {
+        out->links_active[i]++;
+        out->link_mask[i] |= 1u << l;
+      }
     }
     if (out->clique_error[0] != '\0') continue;  // keep enumerating, the clique verdict is already an error
     nvmlGpuFabricInfo_t fi;

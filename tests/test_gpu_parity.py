@@ -609,6 +609,7 @@ def test_topology_agrees_with_the_oracle_on_the_real_nvml(pkg, oracle):
             or all(not o.pci_bus_id[i].value for i in range(o.n))
         assert list(t.mig)[:t.n] == list(o.mig_enabled)[:o.n]
         assert list(t.links_active)[:t.n] == list(o.n_links)[:o.n]
+        assert list(t.link_mask)[:t.n] == [sum(1 << l for l in range(18) if o.link_active[i][l]) for i in range(o.n)]
         assert list(t.fabric_state)[:t.n] == list(o.fabric_state)[:o.n]
         assert t.clique_id.decode() == o.clique_id.decode()
         assert bool(t.clique_error) == bool(o.clique_err)
@@ -643,8 +644,9 @@ FAULTS = [
 ]
 
 
+@pytest.mark.parametrize("real_peers", [False, True], ids=["same-device", "real-nvlink"])
 @pytest.mark.parametrize("name,scenario,unmaps,flags", FAULTS, ids=[f[0] for f in FAULTS])
-def test_kernel_matrix_under_faults_equals_oracle_matrix(pkg, oracle, tmp_path, name, scenario, unmaps, flags):
+def test_kernel_matrix_under_faults_equals_oracle_matrix(pkg, oracle, tmp_path, name, scenario, unmaps, flags, real_peers):
     """the boolean half of parity under faults used to be oracle vs the product's NVML
     walk only.  Here the fault is injected on the DEVICE side (mappings torn down: the loads/stores of that
     pair cannot happen; MIG: no peer mapping at all) and the matrix the kernels produce must equal, bit for
@@ -652,8 +654,13 @@ def test_kernel_matrix_under_faults_equals_oracle_matrix(pkg, oracle, tmp_path, 
     a GPU, P2P disabled for a pair, MIG mode).  The kernels treat a pair as one unit — a torn mapping in
     either direction zeroes both cells — so the NVML scenarios state the fault for both ordered pairs."""
     n, nbytes = 4, 1 << 20
+    if real_peers and NGPU < n:
+        pytest.skip("needs 4 GPUs")
     exp = _oracle_reach_for(tmp_path, scenario, n)
-    with pkg.Open(pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME | flags, ctas=8, timeout_ms=20000)) as p:
+    # same-device: four ranks on GPU 0 (runs on a 1-GPU box); real-nvlink: four GPUs, cooperative launch, 148 CTAs
+    cfg = (pkg.Config(ordinals=list(range(n)), bytes=nbytes, flags=flags, timeout_ms=20000) if real_peers else
+           pkg.Config(ordinals=[0] * n, bytes=nbytes, flags=SAME | flags, ctas=8, timeout_ms=20000))
+    with pkg.Open(cfg) as p:
         for local, peer in unmaps:
             p.UnmapPeer(local, peer)
         r = p.Run()

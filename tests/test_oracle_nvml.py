@@ -23,6 +23,7 @@ CHILD = textwrap.dedent(
     n = r.n
     print(json.dumps({
         "rc": rc, "n": n, "reach": r.reach_matrix(), "n_links": list(r.n_links)[:n],
+        "link_mask": [sum(1 << l for l in range(18) if r.link_active[i][l]) for i in range(n)],
         "mig": list(r.mig_enabled)[:n], "clique_id": r.clique_id.decode(), "clique_err": r.clique_err,
         "clique_err_text": r.clique_err_text.decode(), "imex_gate": r.imex_gate, "calls": r.nvml_calls,
         "uuids": r.uuids(), "name0": r.name[0].value.decode() if n else "", "cc": [r.cc_major[0], r.cc_minor[0]],
@@ -241,6 +242,7 @@ TOPO_CHILD = textwrap.dedent(
         t = m.topology(strict=bool(int(sys.argv[1])))
         print(json.dumps({"rc": 0, "n": t.n, "uuids": [t.uuid[i].value.decode() for i in range(t.n)],
                           "mig": list(t.mig)[:t.n], "links": list(t.links_active)[:t.n],
+                          "link_mask": list(t.link_mask)[:t.n],
                           "clique_id": t.clique_id.decode(), "clique_error": t.clique_error.decode(),
                           "pci": [t.pci_bus_id[i].value.decode() for i in range(t.n)]}))
     except m.ProbeError as e:
@@ -274,6 +276,8 @@ def test_product_topology_agrees_with_oracle(pkg, tmp_path, scenario, strict):
     assert t["rc"] == 0 and o["rc"] == 0
     assert t["n"] == o["n"] and t["uuids"] == o["uuids"]
     assert t["mig"] == o["mig"] and t["links"] == o["n_links"]
+    assert t["link_mask"] == o["link_mask"]  # WHICH physical link is down, not only how many are up
+    assert all(bin(m).count("1") == k for m, k in zip(t["link_mask"], t["links"]))
     assert t["clique_id"] == o["clique_id"]
     assert bool(t["clique_error"]) == bool(o["clique_err"])
     if t["clique_error"]:
