@@ -259,3 +259,120 @@ def test_run_loop_reprobes_on_sigusr1_and_exits_on_sigterm(tmp_path):
             p.kill()
     assert p.returncode == 0 and "Exiting" in err
     assert err.count("t_fabric_probe") >= 2
+
+
+# ---- the daemon's run loop on a box WITHOUT a GPU: a test double of libcdprobe.so (tests/c/fake_cdprobe.c) ----------
+@pytest.fixture(scope="module")
+def fake_lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("fake") / "libfake_cdprobe.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-O1", "-Wall", os.path.join(ROOT, "tests", "c", "fake_cdprobe.c"), "-o", str(out)],
+                   check=True)
+    return str(out)
+
+
+def fake_env(tmp_path, fake_lib, script, **kw):
+    e = {"PATH": os.environ.get("PATH", ""), "COMPUTE_DOMAIN_UUID": "cd-1", "CDPROBE_LIBRARY": fake_lib, "POD_UID": "pod-9",
+         "FABRIC_PROBE_VERDICT_PATH": str(tmp_path / "fabricprobe.json"), "FAKE_CDPROBE_SCRIPT": script,
+         "FAKE_CDPROBE_LOG": str(tmp_path / "calls.log"), "CDPROBE_NVML_PATH": "/nonexistent"}
+    e.update(kw)
+    return e
+
+
+def calls(tmp_path):
+    p = tmp_path / "calls.log"
+    return p.read_text().split("\n")[:-1] if p.exists() else []
+
+
+@pytest.mark.parametrize("script,ok,needle", [
+    ("ok", True, "fabric probe: verdict ok, 2 GPU(s), 0 unreachable pair(s), 0 slow pair(s), min read 674 GB/s"),
+    ("slow", False, "fabric probe: verdict FAILED, 2 GPU(s), 0 unreachable pair(s), 2 slow pair(s), min read 310 GB/s"),
+    ("unreachable", False, "2 unreachable pair(s), 0 slow pair(s)"),
+])
+def test_run_once_through_the_real_writer(tmp_path, fake_lib, script, ok, needle):
+    """`run --once` end to end on CPU: the verdict file the real run path writes matches the Go struct key for key,
+    carries the pod uid, and `check` answers accordingly — a slow-but-reachable domain is NotReady with its own text."""
+    env = fake_env(tmp_path, fake_lib, script)
+    r = subprocess.run([DAEMON, "run", "--once"], env=env, capture_output=True, text=True, timeout=60)
+    assert r.returncode == (0 if ok else 2) and needle in r.stderr, r.stderr
+    d = json.loads((tmp_path / "fabricprobe.json").read_text())
+    assert set(d) == set(go_verdict_schema()) and d["ok"] is ok and d["pod_uid"] == "pod-9" and d["n"] == 2
+    assert d["slow_pairs"] == (2 if script == "slow" else 0) and d["gate_gbps_read"] == 604.0
+    c = daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": env["FABRIC_PROBE_VERDICT_PATH"], "POD_UID": "pod-9"})
+    assert c.returncode == (0 if ok else 1)
+    if script == "slow":
+        assert "fabric probe failed: 0 unreachable pair(s), 2 slow pair(s), min read 310 GB/s, min write 705 GB/s" in c.stderr
+    assert calls(tmp_path) == ["open 1", f"{script} 1", "close 1"]
+
+
+def test_run_loop_reopens_after_a_timeout_and_reprobes_on_signal(tmp_path, fake_lib):
+    """after a timed-out pass the handle may be sticky.  The loop writes a well-formed FAILING verdict
+    for that pass, closes the handle, opens a fresh one for the next pass (SIGUSR1 = a daemon-set change), writes the
+    passing verdict, and leaves on SIGTERM with every handle closed.  No signal is lost (sigsuspend-style wait)."""
+    import signal
+    import time
+
+    env = fake_env(tmp_path, fake_lib, "timeout,ok")
+    v = tmp_path / "fabricprobe.json"
+    p = subprocess.Popen([DAEMON, "run"], env=env, stderr=subprocess.PIPE, text=True)
+    try:
+        t_end = time.time() + 30
+        while not v.exists() and time.time() < t_end:
+            time.sleep(0.02)
+        first = json.loads(v.read_text())
+        assert first["ok"] is False and "probe timed out" in first["error"] and "device watchdog fired" in first["error"]
+        assert first["n"] == 2 and first["reach_read"] == [0, 0, 0, 0]  # the zeroed result of the failed pass, not garbage
+        assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": str(v), "POD_UID": "pod-9"}).returncode == 1
+        time.sleep(0.2)  # let the loop reach its wait
+        p.send_signal(signal.SIGUSR1)
+        t_end = time.time() + 30
+        while time.time() < t_end and not json.loads(v.read_text())["ok"]:
+            time.sleep(0.02)
+        assert json.loads(v.read_text())["ok"] is True
+        assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": str(v), "POD_UID": "pod-9"}).returncode == 0
+        p.send_signal(signal.SIGTERM)
+        err = p.communicate(timeout=30)[1]
+    finally:
+        if p.poll() is None:
+            p.kill()
+    assert p.returncode == 0 and "Exiting" in err and err.count("t_fabric_probe") == 2
+    assert calls(tmp_path) == ["open 1", "timeout 1", "close 1", "open 2", "ok 2", "close 2"]
+
+
+def test_run_loop_periodic_passes_and_burst_of_signals(tmp_path, fake_lib):
+    """FABRIC_PROBE_INTERVAL_S: a pass every second without any signal; a burst of SIGUSR1 coalesces but is never lost."""
+    import signal
+    import time
+
+    env = fake_env(tmp_path, fake_lib, "ok", FABRIC_PROBE_INTERVAL_S="1")
+    p = subprocess.Popen([DAEMON, "run"], env=env, stderr=subprocess.PIPE, text=True)
+    try:
+        time.sleep(2.6)
+        n_periodic = len([c for c in calls(tmp_path) if c.startswith("ok")])
+        assert 2 <= n_periodic <= 4
+        for _ in range(5):
+            p.send_signal(signal.SIGUSR1)
+        time.sleep(0.5)
+        assert len([c for c in calls(tmp_path) if c.startswith("ok")]) >= n_periodic + 1
+        p.send_signal(signal.SIGTERM)
+        err = p.communicate(timeout=30)[1]
+    finally:
+        if p.poll() is None:
+            p.kill()
+    assert p.returncode == 0 and "Exiting" in err
+    assert calls(tmp_path)[0] == "open 1" and calls(tmp_path)[-1] == "close 1"  # one handle for the whole life: no pass failed
+
+
+def test_open_failure_is_not_ready_but_unsupported_does_not_gate(tmp_path, fake_lib):
+    env = fake_env(tmp_path, fake_lib, "openfail,ok")
+    v = tmp_path / "fabricprobe.json"
+    v.write_text(json.dumps({"ok": True, "time_unix": 5}))  # a stale ok:true from a previous pod must not survive
+    r = subprocess.run([DAEMON, "run", "--once"], env=env, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "error opening fabric probe: CUDA call failed: fake: cuMemCreate" in r.stderr
+    d = json.loads(v.read_text())
+    assert d["ok"] is False and "cdprobe_open: CUDA call failed" in d["error"] and d["pod_uid"] == "pod-9"
+    assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": str(v), "POD_UID": "pod-9"}).returncode == 1
+    # unsupported (no sm_100 GPU): no verdict at all, check does not gate — and the stale file is gone too
+    v.write_text(json.dumps({"ok": False, "time_unix": 5, "unreachable_pairs": 3}))
+    r = subprocess.run([DAEMON, "run", "--once"], env=fake_env(tmp_path, fake_lib, "unsupported"), capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "fabric probe not supported on this node" in r.stderr and not v.exists()
+    assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": str(v)}).returncode == 0
