@@ -376,3 +376,78 @@ def test_open_failure_is_not_ready_but_unsupported_does_not_gate(tmp_path, fake_
     r = subprocess.run([DAEMON, "run", "--once"], env=fake_env(tmp_path, fake_lib, "unsupported"), capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "fabric probe not supported on this node" in r.stderr and not v.exists()
     assert daemon(["check"], {"CLIQUE_ID": "", "FABRIC_PROBE_VERDICT_PATH": str(v)}).returncode == 0
+
+
+# ---- the closest thing to `go vet` without a Go toolchain: lexical checks that catch whole classes of compile errors ----
+GO_FILES = [os.path.join(ROOT, "integration", *p) for p in (
+    ("cmd", "compute-domain-daemon", "fabricprobe.go"), ("pkg", "fabricprobe", "fabricprobe.go"),
+    ("pkg", "fabricprobe", "fabricprobe_stub.go"), ("pkg", "featuregates", "fabricprobe_gate.go"),
+    ("pkg", "metrics", "fabricprobe.go"), ("internal", "common", "topology.go"))]
+
+
+def _go_strip(src):
+    """Go source with comments, strings, runes and the cgo preamble blanked out (lengths preserved)."""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        c = src[i]
+        two = src[i:i + 2]
+        if two == "//":
+            j = src.find("\n", i)
+            j = n if j < 0 else j
+            out.append(" " * (j - i))
+            i = j
+        elif two == "/*":
+            j = src.find("*/", i + 2)
+            j = n if j < 0 else j + 2
+            out.append("".join("\n" if ch == "\n" else " " for ch in src[i:j]))
+            i = j
+        elif c in "\"`'":
+            j = i + 1
+            while j < n and src[j] != c:
+                j += 2 if (src[j] == "\\" and c != "`") else 1
+            out.append(c + "".join("\n" if ch == "\n" else " " for ch in src[i + 1:j]) + c)
+            i = j + 1
+        else:
+            out.append(c)
+            i += 1
+    return "".join(out)
+
+
+@pytest.mark.parametrize("path", GO_FILES, ids=[os.path.relpath(p, ROOT) for p in GO_FILES])
+def test_go_file_is_lexically_sound(path):
+    """Balanced brackets, a package clause, and — Go rejects both — no import that is never used and no package
+    qualifier that was never imported."""
+    import re
+
+    src = open(path).read()
+    code = _go_strip(src)
+    stack = []
+    pairs = {")": "(", "]": "[", "}": "{"}
+    for k, ch in enumerate(code):
+        if ch in "([{":
+            stack.append((ch, k))
+        elif ch in ")]}":
+            assert stack and stack[-1][0] == pairs[ch], f"unbalanced {ch!r} at line {code[:k].count(chr(10)) + 1}"
+            stack.pop()
+    assert not stack, f"unclosed {stack[-1][0]!r} opened at line {code[:stack[-1][1]].count(chr(10)) + 1}"
+    assert re.search(r"^package \w+$", code, re.M)
+    # imports: (alias, path) pairs from the original source (paths are strings, blanked in `code`)
+    imports = []
+    for block in re.findall(r"^import \((.*?)^\)", src, re.M | re.S):
+        imports += re.findall(r"^\s*(?:(\w+)\s+)?\"([^\"]+)\"", block, re.M)
+    imports += [(a, p) for a, p in re.findall(r"^import (?:(\w+)\s+)?\"([^\"]+)\"", src, re.M)]
+    assert imports or "import" not in code
+    special = {"k8s.io/klog/v2": "klog", "github.com/urfave/cli/v2": "cli"}
+    names = {}
+    for alias, ipath in imports:
+        names[alias or special.get(ipath, ipath.rsplit("/", 1)[-1])] = ipath
+    body = code[code.index("\n", max(code.rfind("import ("), 0)):]
+    for name, ipath in names.items():
+        assert re.search(rf"\b{re.escape(name)}\.", body), f"{ipath} imported and not used"
+    # every lower-case package qualifier in use is imported (catches a forgotten import)
+    known = set(names) | {"C"}
+    used = set(re.findall(r"(?<![\w.)\]])([a-z][a-z0-9]*)\.[A-Z]\w*", body))
+    locals_ = set(re.findall(r"\b([a-z]\w*)\s*(?::=|,|\))", body)) | set(re.findall(r"\b([a-z]\w*) \*?[\w.\[\]]+[,)]", body))
+    for q in used - known - locals_:
+        # receivers, struct values and parameters (v.OK, res.N, flags.podUID, cfg.Bytes ...) are not packages
+        assert re.search(rf"\b(?:var\s+{q}\b|{q}\s*:?=|func\s*\(\s*{q}\s|\b{q}\s+[\w.*\[\]]+\s*[,)]|\b{q},)", body), f"{q}. used but never imported or declared"
