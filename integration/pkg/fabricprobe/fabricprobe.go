@@ -137,6 +137,9 @@ func Open(cfg Config) (*Probe, error) {
 	if rc := C.cdp_load(cpath); rc != 0 {
 		return nil, fmt.Errorf("%w: cannot load %s (rc=%d)", ErrUnsupported, path, int(rc))
 	}
+	if len(cfg.Ordinals) > C.CDPROBE_MAX_GPUS {
+		return nil, fmt.Errorf("fabricprobe: %d ordinals, the ABI carries at most %d", len(cfg.Ordinals), C.CDPROBE_MAX_GPUS)
+	}
 	var c C.cdprobe_config_t
 	c.abi = C.CDPROBE_ABI_VERSION
 	c.n_gpus = C.uint32_t(len(cfg.Ordinals))
