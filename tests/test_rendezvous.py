@@ -64,3 +64,38 @@ def test_tcp_session_syntax(pkg):
     lib = pkg.abi.load_library()
     assert lib.cdprobe_rendezvous_selftest(b"tcp:nohostport", 0, 2, 200) == pkg.abi.ERR_RENDEZVOUS
     assert lib.cdprobe_rendezvous_selftest(f"tcp:127.0.0.1:{_free_port()}".encode(), 1, 2, 300) == pkg.abi.ERR_RENDEZVOUS
+
+
+def test_silent_or_bogus_connections_do_not_stall_or_join_the_rendezvous(pkg):
+    """ADVICE r01 (rendezvous hardening): a process that connects to the hub and says nothing gets one second, not
+    the whole budget; one that sends a wrong hello is dropped; neither takes a rank, and the real peer still joins.
+    (The same-user check — SO_PEERCRED — cannot be provoked from one uid; the test pins that same-uid peers pass.)"""
+    import socket
+    import struct
+    import time
+
+    session = f"t-{uuid.uuid4().hex[:12]}"
+    hub = subprocess.Popen([sys.executable, "-c", CHILD, session, "0", "2"])
+    addr = b"\0cdprobe." + session.encode()
+    silent = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    t_end = time.time() + 20
+    while True:  # wait for the hub to listen
+        try:
+            silent.connect(addr)
+            break
+        except OSError:
+            assert time.time() < t_end and hub.poll() is None
+            time.sleep(0.05)
+    bogus = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    bogus.connect(addr)
+    bogus.sendall(struct.pack("<II", 0xDEADBEEF, 1))  # wrong magic, claims rank 1
+    again = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    again.connect(addr)
+    again.sendall(struct.pack("<II", 0xCD9B0B01, 7))  # right magic, rank outside the world
+    t0 = time.time()
+    peer = subprocess.Popen([sys.executable, "-c", CHILD, session, "1", "2"])
+    assert peer.wait(timeout=60) == 0 and hub.wait(timeout=60) == 0
+    # the real peer joined although three junk connections were queued ahead of it, and the silent one cost ~1 s, not 20
+    assert time.time() - t0 < 15
+    for s in (silent, bogus, again):
+        s.close()
