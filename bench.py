@@ -37,8 +37,8 @@ if ROOT not in sys.path:
 
 GIB = 1 << 30
 NVLINK_PEAK_GBPS = 900.0        # nominal per direction per GPU
-NVLINK_GUIDE_CE_GBPS = 770.0    # the profiling guide's peer-copy figure; the line carries the SAME-BOX copy-engine
-                                # numbers measured next to the probe (roofline.peak_measured_ce_{uni,bidi})
+# (the profiling guide quotes a 770 GB/s peer copy; it is not used: every N > 1 line carries the SAME-BOX copy-engine
+#  figures measured next to the probe on the probe's own buffers, roofline.peak_measured_ce_{uni,bidi})
 HBM_FALLBACK_GBPS = 6650.0
 # Bytes on the NVLink wire per payload byte of SM-issued traffic, from ncu's nvltx/nvlrx counters on the solo probe
 # kernel (profiles/r02_ncu_nvlink_{read,write}.csv; 1 GiB of payload each): a read costs 1.125 B of response in the
